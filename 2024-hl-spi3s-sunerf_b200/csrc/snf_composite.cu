@@ -1,0 +1,562 @@
+// Front-to-back compositing heads, their analytic backward, the render epilogue, SimpleStar and the loss.
+// All HBM-bound: one warp per ray, coalesced row loads, warp-shuffle scans (double accumulators, which is
+// what torch's CPU cumsum/cumprod use), results staged in the warp's slice of shared memory.
+//   K5  composite_emission_{fwd,bwd} : sunerf/rendering/emission.py:14-54, base_tracing.py:135-156
+//   K6  composite_dt_{fwd,bwd}       : sunerf/rendering/density_temperature.py:192-271
+//   render_epilogue_kernel           : sunerf/rendering/base_tracing.py:91-111, :43-44; density_temperature.py:273-274
+//   simple_star_kernel               : sunerf/model/stellar_model.py:53-102
+//   loss kernels                     : sunerf/model/sunerf.py:98-131, 173-206; sunerf/train/scaling.py:17-28
+#include "snf_common.cuh"
+
+namespace snf {
+
+constexpr int kRayWarps = 4;  // warps (= rays) per CTA for the per-ray kernels
+
+// ------------------------------------------------------------------------------------------------ K5
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_emission_fwd_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
+                                  const float *__restrict__ rays_d, int64_t N, int S, float *__restrict__ image,
+                                  float *__restrict__ weights, float *__restrict__ absorption) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  float *zs = sm + (size_t)warp * 2 * S, *Ps = zs + S;
+  for (int j = lane; j < S; j += 32) zs[j] = z[ray * S + j];
+  const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
+  const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));      // :29
+  __syncwarp();
+  double carry = 1.0, isum = 0.0;
+  for (int base = 0; base < S; base += 32) {
+    const int j = base + lane;
+    const bool ok = j < S;
+    float P = 0.f, f = 1.f;
+    if (ok) {
+      const float dz = fmul(j == 0 ? fsub(zs[1], zs[0]) : fsub(zs[j], zs[j - 1]), dnorm);   // :24-29
+      const float2 r = raw[ray * S + j];
+      const float E = fmul(expf(r.x), dz);                                                   // :34
+      const float a = expf(fmul(-fmaxf(r.y, 0.f), dz));                                      // :37
+      absorption[ray * S + j] = a;
+      f = fadd(a, 1e-10f);                                                                   // :43
+      P = E;
+    }
+    const double incl = warp_incl_prod((double)f, lane);
+    double excl = shfl_up_d(incl, 1);
+    if (lane == 0) excl = 1.0;
+    const float T = (float)(carry * excl);     // exclusive cumprod, double accumulate -> float per prefix
+    P = fmul(P, T);                                                                           // :46
+    if (ok) { Ps[j] = P; isum += (double)P; }
+    carry *= __shfl_sync(kFull, incl, 31);
+  }
+  const float I = (float)warp_sum(isum);                                                      // :48
+  if (lane == 0) image[ray] = I;
+  const float den = fadd(I, 1e-10f);
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) weights[ray * S + j] = fdiv(Ps[j], den);                 // :51-52
+}
+
+// dI/draw0[k] = P_k ; dI/draw1[j] = -1[raw1>0] dz_j a_j (sum_{k>j} P_k)/(a_j+1e-10) ; plus dL/da from g_absorption
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_emission_bwd_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
+                                  const float *__restrict__ rays_d, int64_t N, int S,
+                                  const float *__restrict__ g_image, const float *__restrict__ g_abs,
+                                  float2 *__restrict__ g_raw) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  float *zs = sm + (size_t)warp * 4 * S, *Ps = zs + S, *As = Ps + S, *Dz = As + S;
+  for (int j = lane; j < S; j += 32) zs[j] = z[ray * S + j];
+  const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
+  const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));
+  const float g = g_image[ray];
+  __syncwarp();
+  double carry = 1.0;
+  for (int base = 0; base < S; base += 32) {
+    const int j = base + lane;
+    const bool ok = j < S;
+    float E = 0.f, f = 1.f, a = 1.f, dz = 0.f;
+    if (ok) {
+      dz = fmul(j == 0 ? fsub(zs[1], zs[0]) : fsub(zs[j], zs[j - 1]), dnorm);
+      const float2 r = raw[ray * S + j];
+      E = fmul(expf(r.x), dz);
+      a = expf(fmul(-fmaxf(r.y, 0.f), dz));
+      f = fadd(a, 1e-10f);
+    }
+    const double incl = warp_incl_prod((double)f, lane);
+    double excl = shfl_up_d(incl, 1);
+    if (lane == 0) excl = 1.0;
+    const float T = (float)(carry * excl);
+    if (ok) { Ps[j] = fmul(E, T); As[j] = a; Dz[j] = dz; }
+    carry *= __shfl_sync(kFull, incl, 31);
+  }
+  __syncwarp();
+  // reverse pass: exclusive suffix sums of P
+  double rcarry = 0.0;
+  const int nchunk = (S + 31) / 32;
+  for (int c = nchunk - 1; c >= 0; --c) {
+    const int j = c * 32 + lane;
+    const bool ok = j < S;
+    const double p = ok ? (double)Ps[j] : 0.0;
+    const double suf = warp_suffix_sum(p, lane) + rcarry;   // inclusive
+    const double suf_excl = suf - p;
+    if (ok) {
+      const float2 r = raw[ray * S + j];
+      const float a = As[j];
+      float ga = (float)((double)g * suf_excl / (double)fadd(a, 1e-10f));
+      if (g_abs != nullptr) ga += g_abs[ray * S + j];
+      float2 o;
+      o.x = g * Ps[j];
+      o.y = (r.y > 0.f) ? -ga * Dz[j] * a : 0.f;
+      g_raw[ray * S + j] = o;
+    }
+    rcarry = __shfl_sync(kFull, suf, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+struct DtTables {
+  float x[SNF_TABLE_LEN];
+  float y[SNF_N_AIA][SNF_TABLE_LEN];
+  float slope[SNF_N_AIA][SNF_TABLE_LEN - 1];
+  float kappa[SNF_N_AIA];      // relu(log_abs)
+  float kappa_on[SNF_N_AIA];   // 1[log_abs > 0]
+};
+
+__device__ __forceinline__ void dt_load_tables(DtTables *t, const float *table_x, const float *table_y,
+                                               const float *log_abs) {
+  for (int i = threadIdx.x; i < SNF_TABLE_LEN; i += blockDim.x) t->x[i] = table_x[i];
+  for (int i = threadIdx.x; i < SNF_N_AIA * SNF_TABLE_LEN; i += blockDim.x)
+    t->y[i / SNF_TABLE_LEN][i % SNF_TABLE_LEN] = table_y[i];
+  for (int i = threadIdx.x; i < SNF_N_AIA * (SNF_TABLE_LEN - 1); i += blockDim.x) {
+    const int k = i / (SNF_TABLE_LEN - 1), s = i % (SNF_TABLE_LEN - 1);
+    // xitorch LinearInterp1D: per-segment slope (y[1:]-y[:-1])/(x[1:]-x[:-1])
+    t->slope[k][s] = fdiv(fsub(table_y[k * SNF_TABLE_LEN + s + 1], table_y[k * SNF_TABLE_LEN + s]),
+                          fsub(table_x[s + 1], table_x[s]));
+  }
+  if (threadIdx.x < SNF_N_AIA) {
+    const float la = log_abs[threadIdx.x];
+    t->kappa[threadIdx.x] = fmaxf(la, 0.f);                         // density_temperature.py:256
+    t->kappa_on[threadIdx.x] = la > 0.f ? 1.f : 0.f;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int dt_channel(float wl) {   // wavelength value -> row of the response table
+  const int w = (int)wl;
+  switch (w) {
+    case 94: return 0; case 131: return 1; case 171: return 2; case 193: return 3;
+    case 211: return 4; case 304: return 5; case 335: return 6; default: return -1;
+  }
+}
+
+// segment lookup shared by all channels of a sample: idxl in [0,99] or -1 when theta is outside [x0, x100]
+__device__ __forceinline__ int dt_segment(const DtTables *t, float th) {
+  if (!(th >= t->x[0]) || !(th <= t->x[SNF_TABLE_LEN - 1])) return -1;   // extrap=0 (also NaN)
+  int g = (int)((th - t->x[0]) * 20.f);                 // grid step 0.05; corrected against the table below
+  g = min(max(g, 0), SNF_TABLE_LEN - 2);
+  // searchsorted(left): idxr = #{x < th} clamped to [1,100]; idxl = idxr-1, i.e. x[idxl] < th <= x[idxl+1]
+  while (g > 0 && t->x[g] >= th) --g;
+  while (g < SNF_TABLE_LEN - 2 && t->x[g + 1] < th) ++g;
+  return g;
+}
+
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_dt_fwd_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
+                            const float *__restrict__ wavelengths, int64_t N, int S, int C,
+                            const float *__restrict__ log_abs, const float *__restrict__ vol_c,
+                            const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
+                            float *__restrict__ image, float *__restrict__ weights, float *__restrict__ regq) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  DtTables *tab = reinterpret_cast<DtTables *>(smraw);
+  float *sm = reinterpret_cast<float *>(smraw + sizeof(DtTables));
+  dt_load_tables(tab, table_x, table_y, log_abs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  float *zs = sm + (size_t)warp * 5 * S, *rho = zs + S, *dxq = rho + S, *tau = dxq + S;
+  int *seg = reinterpret_cast<int *>(tau + S);
+  const float vc = vol_c[0];
+  double qsum = 0.0;
+  for (int j = lane; j < S; j += 32) {
+    zs[j] = z[ray * S + j];
+    const float2 v = inf[ray * S + j];
+    const float q = fmaxf(v.x, 0.f);
+    rho[j] = expf(q);                                                        // :237
+    const float th = fmaxf(v.y, 0.f);                                        // :241
+    const int s = dt_segment(tab, th);
+    seg[j] = s;
+    dxq[j] = s >= 0 ? fsub(th, tab->x[s]) : 0.f;
+    regq[ray * S + j] = q;                                                   // :271
+    qsum += (double)q;
+  }
+  const float den = fadd((float)warp_sum(qsum), 1e-10f);
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) weights[ray * S + j] = fdiv(fmaxf(inf[ray * S + j].x, 0.f), den);   // :268-269
+  for (int c = 0; c < C; ++c) {
+    const int k = dt_channel(wavelengths[ray * C + c]);
+    if (k < 0) {   // channel absent: response and absorption stay 0 (:243, :251) -> image 0 * vol_c * F
+      if (lane == 0) image[ray * C + c] = fmul(fmul(0.f, vc), F);
+      continue;
+    }
+    const float kap = tab->kappa[k];
+    double carry = 0.0;
+    for (int base = 0; base < S - 1; base += 32) {
+      const int j = base + lane;
+      const bool ok = j < S - 1;
+      double term = 0.0;
+      if (ok)   // cumulative_trapezoid: cumsum(dx*(left+right))/2   :261
+        term = (double)fmul(fsub(zs[j + 1], zs[j]), fadd(fmul(rho[j], kap), fmul(rho[j + 1], kap)));
+      const double inc = warp_incl_sum(term, lane) + carry;
+      if (ok) {
+        const float A = fdiv((float)inc, 2.f);
+        const int s = seg[j];
+        const float R = s >= 0 ? fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s])) : 0.f;
+        const float em = fmul(fmul(rho[j], rho[j]), R);                      // :263
+        tau[j] = fmul(expf(-A), em);                                         // :264
+      }
+      carry = __shfl_sync(kFull, inc, 31);
+    }
+    __syncwarp();
+    double part = 0.0;   // trapezoid over z[0..S-2]: sum(dx*(left+right))/2   :265
+    for (int j = lane; j < S - 2; j += 32) part += (double)fmul(fsub(zs[j + 1], zs[j]), fadd(tau[j], tau[j + 1]));
+    const float J = fdiv((float)warp_sum(part), 2.f);
+    if (lane == 0) image[ray * C + c] = fmul(fmul(J, vc), F);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_dt_bwd_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
+                            const float *__restrict__ wavelengths, int64_t N, int S, int C,
+                            const float *__restrict__ log_abs, const float *__restrict__ vol_c,
+                            const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
+                            const float *__restrict__ g_image, const float *__restrict__ g_regq,
+                            float2 *__restrict__ g_inf, float *__restrict__ g_log_abs, float *__restrict__ g_vol_c) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  DtTables *tab = reinterpret_cast<DtTables *>(smraw);
+  float *blk_acc = reinterpret_cast<float *>(smraw + sizeof(DtTables));   // [8]: 7 kappa grads + vol_c grad
+  float *sm = blk_acc + 8;
+  if (threadIdx.x < 8) blk_acc[threadIdx.x] = 0.f;
+  dt_load_tables(tab, table_x, table_y, log_abs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray < N) {
+    float *zs = sm + (size_t)warp * 9 * S, *rho = zs + S, *dxq = rho + S, *tau = dxq + S, *eA = tau + S,
+          *Gs = eA + S, *drho = Gs + S, *dth = drho + S;
+    int *seg = reinterpret_cast<int *>(dth + S);
+    const float vc = vol_c[0];
+    for (int j = lane; j < S; j += 32) {
+      zs[j] = z[ray * S + j];
+      const float2 v = inf[ray * S + j];
+      rho[j] = expf(fmaxf(v.x, 0.f));
+      const float th = fmaxf(v.y, 0.f);
+      const int s = dt_segment(tab, th);
+      seg[j] = s;
+      dxq[j] = s >= 0 ? fsub(th, tab->x[s]) : 0.f;
+      drho[j] = 0.f;
+      dth[j] = 0.f;
+    }
+    __syncwarp();
+    float gvc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int k = dt_channel(wavelengths[ray * C + c]);
+      if (k < 0) continue;   // image is the constant 0: no gradient to anything but vol_c (0 * F)
+      const float kap = tab->kappa[k];
+      const float gi = g_image[ray * C + c];
+      double carry = 0.0;
+      for (int base = 0; base < S - 1; base += 32) {
+        const int j = base + lane;
+        const bool ok = j < S - 1;
+        double term = 0.0;
+        if (ok) term = (double)fmul(fsub(zs[j + 1], zs[j]), fadd(fmul(rho[j], kap), fmul(rho[j + 1], kap)));
+        const double inc = warp_incl_sum(term, lane) + carry;
+        if (ok) {
+          const float A = fdiv((float)inc, 2.f);
+          const int s = seg[j];
+          const float R = s >= 0 ? fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s])) : 0.f;
+          const float e = expf(-A);
+          eA[j] = e;
+          tau[j] = fmul(e, fmul(fmul(rho[j], rho[j]), R));
+        }
+        carry = __shfl_sync(kFull, inc, 31);
+      }
+      __syncwarp();
+      double part = 0.0;
+      for (int j = lane; j < S - 2; j += 32) part += (double)fmul(fsub(zs[j + 1], zs[j]), fadd(tau[j], tau[j + 1]));
+      const float J = fdiv((float)warp_sum(part), 2.f);
+      gvc += gi * J * F;                       // I = J * vol_c * F
+      const float Gc = gi * vc * F;            // dL/dJ
+      // dL/dA_k = -Gc w_k tau_k, suffix-summed into G_j = sum_{k>=j} dL/dA_k, k in [0, S-2]
+      double rcarry = 0.0;
+      const int n = S - 1, nchunk = (n + 31) / 32;
+      for (int ch = nchunk - 1; ch >= 0; --ch) {
+        const int j = ch * 32 + lane;
+        const bool ok = j < n;
+        double dA = 0.0;
+        if (ok) {
+          const float wk = 0.5f * ((j >= 1 ? zs[j] - zs[j - 1] : 0.f) + (j <= S - 3 ? zs[j + 1] - zs[j] : 0.f));
+          dA = -(double)Gc * wk * tau[j];
+        }
+        const double suf = warp_suffix_sum(dA, lane) + rcarry;
+        if (ok) Gs[j] = (float)suf;
+        rcarry = __shfl_sync(kFull, suf, 0);
+      }
+      __syncwarp();
+      float dkap = 0.f;
+      for (int j = lane; j < S; j += 32) {
+        // absorption_j enters A_k (k>=j) through dx_j/2 and A_k (k>=j-1) through dx_{j-1}/2
+        float dabs = 0.f;
+        if (j <= S - 2) dabs += 0.5f * (zs[j + 1] - zs[j]) * Gs[j];
+        if (j >= 1) dabs += 0.5f * (zs[j] - zs[j - 1]) * Gs[j - 1];
+        float dr = dabs * kap;
+        dkap += dabs * rho[j];
+        if (j <= S - 2) {
+          const float wk = 0.5f * ((j >= 1 ? zs[j] - zs[j - 1] : 0.f) + (j <= S - 3 ? zs[j + 1] - zs[j] : 0.f));
+          const float dem = Gc * wk * eA[j];   // dL/d em_j
+          const int s = seg[j];
+          if (s >= 0) {
+            const float R = fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s]));
+            dr += dem * 2.f * rho[j] * R;
+            dth[j] += dem * rho[j] * rho[j] * tab->slope[k][s];
+          }
+        }
+        drho[j] += dr;
+      }
+      dkap = warp_sum_f(dkap) * tab->kappa_on[k];
+      if (lane == 0 && dkap != 0.f) atomicAdd(&blk_acc[k], dkap);
+      __syncwarp();
+    }
+    gvc = 0.f + gvc;
+    if (lane == 0) atomicAdd(&blk_acc[7], gvc);
+    for (int j = lane; j < S; j += 32) {
+      const float2 v = inf[ray * S + j];
+      float2 o;
+      o.x = v.x > 0.f ? drho[j] * rho[j] + (g_regq != nullptr ? g_regq[ray * S + j] : 0.f) : 0.f;
+      o.y = v.y > 0.f ? dth[j] : 0.f;
+      g_inf[ray * S + j] = o;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 7 && blk_acc[threadIdx.x] != 0.f) atomicAdd(&g_log_abs[threadIdx.x], blk_acc[threadIdx.x]);
+  if (threadIdx.x == 7 && blk_acc[7] != 0.f) atomicAdd(g_vol_c, blk_acc[7]);
+}
+
+// ------------------------------------------------------------------------------------------ epilogue (a10)
+__global__ void __launch_bounds__(kRayWarps * 32)
+    render_epilogue_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                           const float *__restrict__ z, const float *__restrict__ weights,
+                           const float *__restrict__ q, int64_t N, int S, float r0, int kind,
+                           float *__restrict__ height_map, float *__restrict__ absorption_map,
+                           float *__restrict__ reg, float gscale, float *__restrict__ g_q) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  const float o0 = rays_o[3 * ray], o1 = rays_o[3 * ray + 1], o2 = rays_o[3 * ray + 2];
+  const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
+  double hsum = 0.0, asum = 0.0;
+  for (int j = lane; j < S; j += 32) {
+    const float zz = z[ray * S + j];
+    const float p0 = fadd(o0, fmul(d0, zz)), p1 = fadd(o1, fmul(d1, zz)), p2 = fadd(o2, fmul(d2, zz));
+    const float dist = __fsqrt_rn(sum3(fmul(p0, p0), fmul(p1, p1), fmul(p2, p2)));          // :101
+    const float qq = q[ray * S + j];
+    hsum += (double)fmul(weights[ray * S + j], dist);                                         // :102
+    asum += (double)fsub(1.f, qq);                                                            // :99
+    const float over = fmaxf(fsub(dist, r0), 0.f);
+    float r, gq;
+    if (kind == 0) { r = fmul(over, fsub(1.f, qq)); gq = -over * gscale; }                    // base_tracing.py:43-44
+    else { r = fmul(over, fmaxf(qq, 0.f)); gq = qq > 0.f ? over * gscale : 0.f; }             // density_temperature.py:273-274
+    reg[ray * S + j] = r;
+    if (g_q != nullptr) g_q[ray * S + j] = gq;
+  }
+  hsum = warp_sum(hsum);
+  asum = warp_sum(asum);
+  if (lane == 0) { height_map[ray] = (float)hsum; absorption_map[ray] = (float)asum; }
+}
+
+// ------------------------------------------------------------------------------------------ SimpleStar (a7)
+__global__ void __launch_bounds__(256) simple_star_kernel(const float4 *__restrict__ x, int64_t M, float rho_0,
+                                                          float h0, float T0, float R_s, float t_ph,
+                                                          float2 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float4 p = x[i];
+  const float r = __fsqrt_rn(sum3(fmul(p.x, p.x), fmul(p.y, p.y), fmul(p.z, p.z)));          // :73
+  float rho, T;
+  if (r <= 1.0f) {
+    rho = rho_0;                                                                               // :83
+    T = t_ph;                                                                                  // :90
+  } else {
+    rho = fmul(rho_0, expf(fmul(fdiv(1.f, h0), fsub(fdiv(1.f, r), 1.f))));                     // :85
+    T = (r <= R_s) ? fadd(fmul(fsub(r, 1.f), fdiv(fsub(T0, t_ph), fsub(R_s, 1.f))), t_ph) : T0;   // :93, :96
+  }
+  out[i] = make_float2(logf(rho), log10f(T));                                                  // :86, :97
+}
+
+// ------------------------------------------------------------------------------------------ loss (a11)
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }
+
+__global__ void __launch_bounds__(256)
+    train_loss_kernel(const float *__restrict__ coarse, const float *__restrict__ fine,
+                      const float *__restrict__ target, const float *__restrict__ reg, int64_t n_img,
+                      int64_t n_reg, int asinh_scaling, float a, float norm, float lambda_image,
+                      float *__restrict__ acc /*[3]*/, float *__restrict__ g_coarse, float *__restrict__ g_fine,
+                      int *__restrict__ finite_flag) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  float sc = 0.f, sf = 0.f, sr = 0.f;
+  bool bad = false;
+  const float gcoef = 2.f * lambda_image / (float)n_img;   // d(lambda*mean((s-t)^2))/ds
+  for (int64_t i = tid; i < n_img; i += stride) {
+    const float c = coarse[i], f = fine[i], t = target[i];
+    bad |= !finite_f(c) | !finite_f(f);
+    float cs = c, fs = f, ts = t, dc = 1.f, df = 1.f;
+    if (asinh_scaling) {   // ImageAsinhScaling: asinh(x/a)/asinh(1/a), vmax = 1
+      cs = asinhf(c / a) / norm; fs = asinhf(f / a) / norm; ts = asinhf(t / a) / norm;
+      dc = 1.f / (a * norm * sqrtf(1.f + (c / a) * (c / a)));
+      df = 1.f / (a * norm * sqrtf(1.f + (f / a) * (f / a)));
+    }
+    const float ec = cs - ts, ef = fs - ts;
+    sc += ec * ec; sf += ef * ef;
+    g_coarse[i] = gcoef * ec * dc;
+    g_fine[i] = gcoef * ef * df;
+  }
+  for (int64_t i = tid; i < n_reg; i += stride) {
+    const float r = reg[i];
+    bad |= !finite_f(r);
+    sr += r;
+  }
+  sc = warp_sum_f(sc); sf = warp_sum_f(sf); sr = warp_sum_f(sr);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], sc); atomicAdd(&acc[1], sf); atomicAdd(&acc[2], sr); }
+  if (bad) atomicOr(finite_flag, 1);
+}
+
+// acc aliases losses+1 (no __restrict__): all three sums are read before anything is written
+__global__ void train_loss_finalize_kernel(const float *acc, int64_t n_img, int64_t n_reg, float lambda_image,
+                                           float lambda_reg, float *losses) {
+  const float lc = acc[0] / (float)n_img, lf = acc[1] / (float)n_img, lr = acc[2] / (float)n_reg;
+  losses[0] = lambda_image * (lc + lf) + lambda_reg * lr;
+  losses[1] = lc; losses[2] = lf; losses[3] = lr;
+}
+
+}  // namespace snf
+
+using namespace snf;
+
+extern "C" int snf_composite_emission_fwd(const float *raw, const float *z, const float *rays_d, int64_t N, int S,
+                                          float *image, float *weights, float *absorption, void *stream) {
+  SNF_CHECK_PTR(raw); SNF_CHECK_PTR(z); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(image); SNF_CHECK_PTR(weights);
+  SNF_CHECK_PTR(absorption); SNF_CHECK_ALIGN(raw, 8);
+  if (N < 0 || S < 2) return SNF_E_ARG;
+  if (S > 256) return SNF_E_SHAPE;
+  if (N == 0) return 0;
+  composite_emission_fwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32,
+                                  (size_t)kRayWarps * 2 * S * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(raw), z, rays_d, N, S, image, weights, absorption);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_composite_emission_bwd(const float *raw, const float *z, const float *rays_d, int64_t N, int S,
+                                          const float *g_image, const float *g_absorption, float *g_raw,
+                                          void *stream) {
+  SNF_CHECK_PTR(raw); SNF_CHECK_PTR(z); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(g_image); SNF_CHECK_PTR(g_raw);
+  SNF_CHECK_ALIGN(raw, 8); SNF_CHECK_ALIGN(g_raw, 8);
+  if (N < 0 || S < 2) return SNF_E_ARG;
+  if (S > 256) return SNF_E_SHAPE;
+  if (N == 0) return 0;
+  composite_emission_bwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32,
+                                  (size_t)kRayWarps * 4 * S * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(raw), z, rays_d, N, S, g_image, g_absorption,
+      reinterpret_cast<float2 *>(g_raw));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_composite_dt_fwd(const float *inferences, const float *z, const float *wavelengths, int64_t N,
+                                    int S, int C, const float *log_abs, const float *vol_c, const float *table_x,
+                                    const float *table_y, float F, float *image, float *weights, float *regq,
+                                    void *stream) {
+  SNF_CHECK_PTR(inferences); SNF_CHECK_PTR(z); SNF_CHECK_PTR(wavelengths); SNF_CHECK_PTR(log_abs);
+  SNF_CHECK_PTR(vol_c); SNF_CHECK_PTR(table_x); SNF_CHECK_PTR(table_y); SNF_CHECK_PTR(image);
+  SNF_CHECK_PTR(weights); SNF_CHECK_PTR(regq); SNF_CHECK_ALIGN(inferences, 8);
+  if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
+  if (S > 256 || C > 8) return SNF_E_SHAPE;
+  if (N == 0) return 0;
+  const size_t smem = sizeof(DtTables) + (size_t)kRayWarps * 5 * S * sizeof(float);
+  composite_dt_fwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(inferences), z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F,
+      image, weights, regq);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_composite_dt_bwd(const float *inferences, const float *z, const float *wavelengths, int64_t N,
+                                    int S, int C, const float *log_abs, const float *vol_c, const float *table_x,
+                                    const float *table_y, float F, const float *g_image, const float *g_regq,
+                                    float *g_inferences, float *g_log_abs, float *g_vol_c, void *stream) {
+  SNF_CHECK_PTR(inferences); SNF_CHECK_PTR(z); SNF_CHECK_PTR(wavelengths); SNF_CHECK_PTR(log_abs);
+  SNF_CHECK_PTR(vol_c); SNF_CHECK_PTR(table_x); SNF_CHECK_PTR(table_y); SNF_CHECK_PTR(g_image);
+  SNF_CHECK_PTR(g_inferences); SNF_CHECK_PTR(g_log_abs); SNF_CHECK_PTR(g_vol_c);
+  SNF_CHECK_ALIGN(inferences, 8); SNF_CHECK_ALIGN(g_inferences, 8);
+  if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
+  if (S > 256 || C > 8) return SNF_E_SHAPE;
+  if (N == 0) return 0;
+  const size_t smem = sizeof(DtTables) + 8 * sizeof(float) + (size_t)kRayWarps * 9 * S * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(composite_dt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  composite_dt_bwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(inferences), z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F,
+      g_image, g_regq, reinterpret_cast<float2 *>(g_inferences), g_log_abs, g_vol_c);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_render_epilogue(const float *rays_o, const float *rays_d, const float *z_comb,
+                                   const float *weights, const float *q, int64_t N, int S, float r0, int kind,
+                                   float *height_map, float *absorption_map, float *reg, float reg_grad_scale,
+                                   float *g_q, void *stream) {
+  SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(z_comb); SNF_CHECK_PTR(weights); SNF_CHECK_PTR(q);
+  SNF_CHECK_PTR(height_map); SNF_CHECK_PTR(absorption_map); SNF_CHECK_PTR(reg);
+  if (N < 0 || S <= 0 || (kind != 0 && kind != 1)) return SNF_E_ARG;
+  if (N == 0) return 0;
+  render_epilogue_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, z_comb, weights, q, N, S, r0, kind, height_map, absorption_map, reg, reg_grad_scale, g_q);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_simple_star_fwd(const float *x, int64_t M, float rho_0, float h0, float T0, float R_s,
+                                   float t_photosphere, float *out, void *stream) {
+  SNF_CHECK_PTR(x); SNF_CHECK_PTR(out); SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8);
+  if (M < 0) return SNF_E_ARG;
+  if (M == 0) return 0;
+  simple_star_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(x), M, rho_0, h0, T0, R_s, t_photosphere, reinterpret_cast<float2 *>(out));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_train_loss(const float *coarse, const float *fine, const float *target, const float *reg,
+                              int64_t N, int C, int64_t n_reg, int asinh_scaling, float asinh_a,
+                              float lambda_image, float lambda_reg, float *losses, float *g_coarse, float *g_fine,
+                              int *finite_flag, void *stream) {
+  SNF_CHECK_PTR(coarse); SNF_CHECK_PTR(fine); SNF_CHECK_PTR(target); SNF_CHECK_PTR(reg); SNF_CHECK_PTR(losses);
+  SNF_CHECK_PTR(g_coarse); SNF_CHECK_PTR(g_fine); SNF_CHECK_PTR(finite_flag);
+  if (N <= 0 || C <= 0 || n_reg <= 0) return SNF_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  // reentrant without extra scratch: the raw sums accumulate in losses[1..3] and are finalised in place
+  cudaError_t e = cudaMemsetAsync(losses, 0, 4 * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t n_img = N * C;
+  const float norm = (float)asinh(1.0 / (double)asinh_a);   // scaling.py:21
+  const int64_t work = n_img > n_reg ? n_img : n_reg;
+  const unsigned blocks = (unsigned)(ceil_div64(work, 256) < 592 ? ceil_div64(work, 256) : 592);
+  train_loss_kernel<<<blocks, 256, 0, st>>>(coarse, fine, target, reg, n_img, n_reg, asinh_scaling, asinh_a, norm,
+                                            lambda_image, losses + 1, g_coarse, g_fine, finite_flag);
+  train_loss_finalize_kernel<<<1, 1, 0, st>>>(losses + 1, n_img, n_reg, lambda_image, lambda_reg, losses);
+  count_launch(2);
+  return launch_status();
+}

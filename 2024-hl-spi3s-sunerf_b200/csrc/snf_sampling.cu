@@ -1,0 +1,235 @@
+// Ray-sample placement kernels (HBM-bound, fp32 with the reference's exact operation order).
+//   K1 stratified_kernel : StratifiedSampler.forward      sunerf/train/sampling.py:68-102
+//   K2 hier_kernel       : HierarchicalSampler.forward    sunerf/train/sampling.py:111-169
+//   make_query_kernel    : o + d*z, cat time              sampling.py:100, base_tracing.py:64-65
+#include "snf_common.cuh"
+
+namespace snf {
+
+unsigned long long g_launches = 0;
+
+// ------------------------------------------------------------------------------------------------
+// K1: one thread per (ray, sample).  The per-ray scalars (shell entry/exit) are recomputed by every
+// thread of the ray: ~25 flops against 12 B of traffic per element, and it keeps every access of the
+// [N,S] streams perfectly coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict__ rays_o,
+                                                         const float *__restrict__ rays_d,
+                                                         const float *__restrict__ t_vals,
+                                                         const float *__restrict__ t_rand, int64_t N, int S,
+                                                         float D, float solar_R, float *__restrict__ z_out,
+                                                         float *__restrict__ pts_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * S) return;
+  const int64_t i = idx / S;
+  const int j = (int)(idx - i * S);
+  const float o0 = rays_o[3 * i], o1 = rays_o[3 * i + 1], o2 = rays_o[3 * i + 2];
+  const float d0 = rays_d[3 * i], d1 = rays_d[3 * i + 1], d2 = rays_d[3 * i + 2];
+  const float osq = sum3(fmul(o0, o0), fmul(o1, o1), fmul(o2, o2));
+  const float r_obs = __fsqrt_rn(osq);                                            // :74
+  const float qa = sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2));                // :77
+  const float qb = sum3(fmul(fmul(2.f, o0), d0), fmul(fmul(2.f, o1), d1), fmul(fmul(2.f, o2), d2));  // :78
+  const float qc = fsub(osq, fmul(solar_R, solar_R));                             // :80
+  const float disc = fsub(fmul(qb, qb), fmul(fmul(4.f, qa), qc));
+  const float hit = fdiv(fsub(-qb, __fsqrt_rn(disc)), fmul(2.f, qa));             // :81 (NaN on a miss)
+  const float z_near = fsub(r_obs, D);                                            // :83
+  float z_far = fadd(r_obs, D);                                                   // :84
+  if (hit == hit) z_far = hit;                                                    // :87-88
+  auto bin_edge = [&](int k) {                                                    // :90
+    const float t = t_vals[k];
+    return fadd(fmul(z_near, fsub(1.f, t)), fmul(z_far, t));
+  };
+  float z = bin_edge(j);
+  if (t_rand != nullptr) {                                                        // :93-98
+    const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
+    const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
+    z = fadd(lo, fmul(fsub(hi, lo), t_rand[idx]));
+  }
+  z_out[idx] = z;
+  if (pts_out != nullptr) {                                                       // :100
+    pts_out[3 * idx] = fadd(o0, fmul(d0, z));
+    pts_out[3 * idx + 1] = fadd(o1, fmul(d1, z));
+    pts_out[3 * idx + 2] = fadd(o2, fmul(d2, z));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: one warp per ray.  The ray's z, bin centres, CDF and the new samples live in the warp's slice of
+// shared memory; the CDF is a warp scan in double (bit-equal to torch's CPU cumsum, which accumulates in
+// double: every partial sum of these 62 addends is exactly representable, so association is irrelevant),
+// the inverse CDF is a binary search per new sample, and the 64+128 merge is a rank merge (two binary
+// searches) with a sortedness check and an odd-even-sort fallback so the result always equals torch.sort.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_vals,
+                                                   const float *__restrict__ weights,
+                                                   const float *__restrict__ u, const float *__restrict__ cdf_in,
+                                                   int64_t N, int S, int n_new, float *__restrict__ new_z,
+                                                   float *__restrict__ z_comb, int64_t *__restrict__ inds,
+                                                   float *__restrict__ cdf_out) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (ray >= N) return;  // whole warp exits together; only __syncwarp below
+  const int T = S + n_new;
+  float *zs = sm + (size_t)warp * (3 * S + n_new + T);
+  float *bins = zs + S, *cdf = bins + S, *nz = cdf + S, *comb = nz + n_new;
+  const int nc = S - 1;  // CDF length == number of bin centres
+
+  for (int j = lane; j < S; j += 32) zs[j] = z_vals[ray * S + j];
+  __syncwarp();
+  for (int j = lane; j < nc; j += 32) bins[j] = fmul(.5f, fadd(zs[j + 1], zs[j]));   // :118
+  if (cdf_in != nullptr) {
+    for (int j = lane; j < nc; j += 32) cdf[j] = cdf_in[ray * nc + j];
+  } else {
+    const float *w = weights + ray * S + 1;  // weights[..., 1:-1]  :119
+    const int nw = S - 2;
+    double part = 0.0;
+    for (int j = lane; j < nw; j += 32) part += (double)fadd(w[j], 1e-5f);
+    const float total = (float)warp_sum(part);                                       // :134
+    double carry = 0.0;
+    for (int base = 0; base < nw; base += 32) {                                      // :137
+      const int j = base + lane;
+      const double p = (j < nw) ? (double)fdiv(fadd(w[j], 1e-5f), total) : 0.0;
+      const double inc = warp_incl_sum(p, lane) + carry;
+      if (j < nw) cdf[j + 1] = (float)inc;
+      carry = __shfl_sync(kFull, inc, 31);
+    }
+    if (lane == 0) cdf[0] = 0.f;                                                     // :138
+  }
+  __syncwarp();
+  if (cdf_out != nullptr)
+    for (int j = lane; j < nc; j += 32) cdf_out[ray * nc + j] = cdf[j];
+
+  for (int k = lane; k < n_new; k += 32) {
+    const float uu = u[k];
+    int lo = 0, hi = nc;                       // searchsorted(right=True): #{cdf <= u}   :149
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0), above = min(lo, nc - 1);                       // :152-153
+    const float cb = cdf[below], ca = cdf[above], bb = bins[below], ba = bins[above];
+    float denom = fsub(ca, cb);                                                      // :164
+    if (denom < 1e-5f) denom = 1.f;                                                  // :165
+    const float t = fdiv(fsub(uu, cb), denom);                                       // :166
+    const float s = fadd(bb, fmul(t, fsub(ba, bb)));                                 // :167
+    nz[k] = s;
+    new_z[ray * n_new + k] = s;
+    if (inds != nullptr) inds[ray * n_new + k] = lo;
+  }
+  __syncwarp();
+
+  // ---- sort(cat(z, new_z))  :123
+  bool sorted = true;
+  for (int j = lane; j < S - 1; j += 32) sorted &= (zs[j] <= zs[j + 1]);
+  for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
+  sorted = __all_sync(kFull, sorted);
+  if (sorted) {
+    for (int j = lane; j < S; j += 32) {       // rank of z_j: j + #{new_z < z_j}
+      const float v = zs[j];
+      int lo = 0, hi = n_new;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (nz[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      comb[j + lo] = v;
+    }
+    for (int k = lane; k < n_new; k += 32) {   // rank of new_z_k: k + #{z <= new_z_k}
+      const float v = nz[k];
+      int lo = 0, hi = S;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zs[mid] <= v) lo = mid + 1; else hi = mid;
+      }
+      comb[k + lo] = v;
+    }
+  } else {  // rare: an input is not monotone (rounding at a bin edge, NaN) -> odd-even transposition sort
+    for (int j = lane; j < S; j += 32) comb[j] = zs[j];
+    for (int k = lane; k < n_new; k += 32) comb[S + k] = nz[k];
+    __syncwarp();
+    for (int phase = 0; phase < T; ++phase) {
+      for (int p = 2 * lane + (phase & 1); p + 1 < T; p += 64) {
+        const float a = comb[p], b = comb[p + 1];
+        if (!(a <= b) && (b == b)) { comb[p] = b; comb[p + 1] = a; }   // NaNs sink to the end like torch.sort
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < T; j += 32) z_comb[ray * T + j] = comb[j];
+}
+
+// query[n,s,:] = (o + d*z, t)
+__global__ void __launch_bounds__(256) make_query_kernel(const float *__restrict__ rays_o,
+                                                         const float *__restrict__ rays_d,
+                                                         const float *__restrict__ z,
+                                                         const float *__restrict__ times, int64_t N, int S,
+                                                         float4 *__restrict__ query) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * S) return;
+  const int64_t i = idx / S;
+  const float zz = z[idx];
+  float4 q;
+  q.x = fadd(rays_o[3 * i], fmul(rays_d[3 * i], zz));
+  q.y = fadd(rays_o[3 * i + 1], fmul(rays_d[3 * i + 1], zz));
+  q.z = fadd(rays_o[3 * i + 2], fmul(rays_d[3 * i + 2], zz));
+  q.w = times[i];
+  query[idx] = q;
+}
+
+}  // namespace snf
+
+using namespace snf;
+
+extern "C" int snf_version(void) { return SNF_VERSION; }
+extern "C" int64_t snf_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" const char *snf_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case SNF_E_ARG: return "bad argument (null pointer or non-positive size)";
+    case SNF_E_SHAPE: return "shape not supported by the compiled kernels";
+    case SNF_E_ALIGN: return "pointer alignment";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown";
+  }
+}
+
+extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals,
+                                     const float *t_rand, int64_t N, int S, float distance, float solar_R,
+                                     float *z_vals, float *points, void *stream) {
+  SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(t_vals); SNF_CHECK_PTR(z_vals);
+  if (N < 0 || S <= 0) return SNF_E_ARG;
+  if (N == 0) return 0;
+  const int64_t total = N * S;
+  stratified_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in,
+                                 int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds,
+                                 float *cdf_out, void *stream) {
+  SNF_CHECK_PTR(z_vals); SNF_CHECK_PTR(u); SNF_CHECK_PTR(new_z); SNF_CHECK_PTR(z_comb);
+  if (weights == nullptr && cdf_in == nullptr) return SNF_E_ARG;
+  if (N < 0 || S < 3 || n_new <= 0) return SNF_E_ARG;
+  if (S > 256 || n_new > 512) return SNF_E_SHAPE;
+  if (N == 0) return 0;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (3 * S + n_new + S + n_new) * sizeof(float);
+  hier_kernel<<<(unsigned)ceil_div64(N, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+      z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int snf_make_query(const float *rays_o, const float *rays_d, const float *z, const float *times,
+                              int64_t N, int S, float *query, void *stream) {
+  SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(z); SNF_CHECK_PTR(times); SNF_CHECK_PTR(query);
+  SNF_CHECK_ALIGN(query, 16);
+  if (N < 0 || S <= 0) return SNF_E_ARG;
+  if (N == 0) return 0;
+  make_query_kernel<<<(unsigned)ceil_div64(N * S, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, z, times, N, S, reinterpret_cast<float4 *>(query));
+  count_launch();
+  return launch_status();
+}

@@ -1,0 +1,184 @@
+"""Training fast path: one ray batch -> loss -> analytic backward -> (NCCL all-reduce) -> clip + Adam, without
+autograd and without a host sync.  Same semantics as the reference's Lightning step
+(sunerf/model/sunerf.py:98-131 emission, :173-206 density-temperature; optimiser :30-40; clip run_emission.py:72),
+with Lightning's single-process 'dp' strategy (run_emission.py:69) replaced by one process per GPU, rays
+sharded by rank and ONE all-reduce of the flat fp32 gradient buffer per step.
+
+All parameters of the rendering module are re-homed as views into one flat buffer (16-byte aligned
+segments), so the kernels write gradients in place, NCCL reduces one tensor and the optimiser is one
+pass.  `rendering.state_dict()` keeps the reference's keys and shapes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import SnfError
+from .rendering import DensityTemperatureRadiativeTransfer, SuNeRFRendering
+
+
+class ImageAsinhScaling(torch.nn.Module):
+    """sunerf/train/scaling.py:17-28 (plain torch ops; the fast path fuses it into the loss kernel)."""
+
+    def __init__(self, vmax=1, a=0.005):
+        super().__init__()
+        import numpy as np
+        self.normalization = torch.nn.Parameter(torch.tensor(np.arcsinh(1 / a), dtype=torch.float32), requires_grad=False)
+        self.a = torch.nn.Parameter(torch.tensor(a, dtype=torch.float32), requires_grad=False)
+        self.vmax = torch.nn.Parameter(torch.tensor(vmax, dtype=torch.float32), requires_grad=False)
+
+    def forward(self, image):
+        return torch.asinh(image / self.vmax / self.a) / self.normalization
+
+
+def _align4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class RayTrainer:
+    def __init__(self, rendering: SuNeRFRendering, lr: float = 1e-4, lr_end: float = 1e-5, lr_iterations: float = 1e6,
+                 clip_norm: float = 0.5, lambda_image: float = 1.0, lambda_regularization: float = 1.0,
+                 asinh_a: float = 0.005, process_group=None, device=None):
+        self.r = rendering
+        self.dt = isinstance(rendering, DensityTemperatureRadiativeTransfer)
+        self.dev = torch.device(device) if device is not None else next(rendering.parameters()).device
+        if self.dev.type != 'cuda':
+            raise SnfError('RayTrainer needs the rendering module on a CUDA device')
+        self.lr, self.gamma, self.clip = lr, (lr_end / lr) ** (1 / lr_iterations), clip_norm
+        self.lam_img, self.lam_reg, self.asinh_a = lambda_image, lambda_regularization, asinh_a
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self.step_count = 0
+        self._flatten()
+        self.scratch = torch.zeros(1024, device=self.dev)
+        self.grad_norm = torch.zeros(1, device=self.dev)
+        self.finite_flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self._side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+
+    # -- flat parameter / gradient buffers: [fine model | coarse model], log_abs contiguous in channel order
+    def _flatten(self):
+        segs = []   # (param, offset)
+        off = 0
+        self.model_range = {}
+        for name in ('fine_model', 'coarse_model'):
+            model = getattr(self.r, name)
+            start = off
+            for p in model.linear_params():
+                segs.append((p, off)); off += _align4(p.numel())
+            if self.dt:
+                self.__dict__[f'la_off_{name}'] = off
+                for c in ops.AIA_CHANNELS:
+                    segs.append((model.log_absortpion[str(c)], off)); off += 1
+                off = _align4(off)
+                self.__dict__[f'vc_off_{name}'] = off
+                segs.append((model.volumetric_constant, off)); off += 4
+            self.model_range[name] = (start, off)
+        known = {id(p) for p, _ in segs}
+        extra = [p for p in self.r.parameters() if id(p) not in known and p.requires_grad]
+        if extra:
+            raise SnfError('rendering module has trainable parameters the fast path does not know')
+        self.n_flat = off
+        self.flat = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.grad_view = {}
+        with torch.no_grad():
+            for p, o in segs:
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.detach().reshape(-1).to(self.dev))
+                p.data = self.flat[o:o + n].view(p.shape)
+                self.grad_view[id(p)] = self.flat_grad[o:o + n].view(p.shape)
+
+    def _grads(self, model):
+        ps = model.linear_params()
+        return [self.grad_view[id(p)] for p in ps[0::2]], [self.grad_view[id(p)] for p in ps[1::2]]
+
+    def _field(self, model, query, train=True):
+        ps = model.linear_params()
+        weights, biases = ps[0::2], ps[1::2]
+        packed = model._packed_ptr(weights, biases) if model.precision == 'bf16' else None
+        out, ws = ops.mlp_forward(query.view(-1, 4), weights, biases, model._out_offsets(), mode=model.precision,
+                                  train=train, packed_ptr=packed)
+        return out, ws, weights, packed
+
+    @torch.no_grad()
+    def step(self, rays_o, rays_d, times, target, wavelengths=None, t_rand=None) -> Dict[str, torch.Tensor]:
+        r = self.r
+        N = rays_o.shape[0]
+        z, _ = r.sampler.sample_z(rays_o, rays_d, t_rand=t_rand)
+        S = z.shape[1]
+        q_c = ops.make_query(rays_o, rays_d, z, times)
+        raw_c, ws_c, w_c, pk_c = self._field(r.coarse_model, q_c)
+        raw_c = raw_c.view(N, S, 2)
+        if self.dt:
+            la_c = self.flat[self.la_off_coarse_model:self.la_off_coarse_model + 7]
+            vc_c = self.flat[self.vc_off_coarse_model:self.vc_off_coarse_model + 1]
+            la_f = self.flat[self.la_off_fine_model:self.la_off_fine_model + 7]
+            vc_f = self.flat[self.vc_off_fine_model:self.vc_off_fine_model + 1]
+            F = float(r.pixel_intensity_factor)
+            img_c, wts_c, _ = ops.composite_dt_fwd(raw_c, z, wavelengths, la_c, vc_c, r._table_x, r._table_y, F)
+        else:
+            img_c, wts_c, _ = ops.composite_emission_fwd(raw_c, z, rays_d)
+        new_z, z_comb = r.sampler_hierarchical.resample(z, wts_c)
+        Sf = z_comb.shape[1]
+        q_f = ops.make_query(rays_o, rays_d, z_comb, times)
+        raw_f, ws_f, w_f, pk_f = self._field(r.fine_model, q_f)
+        raw_f = raw_f.view(N, Sf, 2)
+        if self.dt:
+            img_f, wts_f, qq = ops.composite_dt_fwd(raw_f, z_comb, wavelengths, la_f, vc_f, r._table_x, r._table_y, F)
+        else:
+            img_f, wts_f, qq = ops.composite_emission_fwd(raw_f, z_comb, rays_d)
+        _, _, reg, g_q = ops.render_epilogue(rays_o, rays_d, z_comb, wts_f, qq, r.reg_radius / r.Rs_per_ds, r.kind,
+                                             grad_scale=self.lam_reg / float(N * Sf), want_gq=True)
+        losses, g_ic, g_if, _ = ops.train_loss(img_c, img_f, target, reg, asinh_scaling=not self.dt, asinh_a=self.asinh_a,
+                                               lambda_image=self.lam_img, lambda_reg=self.lam_reg,
+                                               finite_flag=self.finite_flag)
+        # ---- backward: fine network first so its gradient bucket can be reduced while the coarse one runs
+        gw, gb = self._grads(r.fine_model)
+        if self.dt:
+            lo, hi = self.la_off_fine_model, self.vc_off_fine_model + 4
+            self.flat_grad[lo:hi].zero_()
+            g_raw_f, _, _ = ops.composite_dt_bwd(raw_f, z_comb, wavelengths, la_f, vc_f, r._table_x, r._table_y, F, g_if, g_q,
+                                                 self.flat_grad[lo:lo + 7], self.flat_grad[hi - 4:hi - 3])
+        else:
+            g_raw_f = ops.composite_emission_bwd(raw_f, z_comb, rays_d, g_if.view(-1), g_q)
+        ops.mlp_backward(q_f.view(-1, 4), w_f, g_raw_f.view(-1, 2), ws_f, gw, gb, packed_ptr=pk_f)
+        h_fine = self._reduce_async('fine_model')
+        gw, gb = self._grads(r.coarse_model)
+        if self.dt:
+            lo, hi = self.la_off_coarse_model, self.vc_off_coarse_model + 4
+            self.flat_grad[lo:hi].zero_()
+            g_raw_c, _, _ = ops.composite_dt_bwd(raw_c, z, wavelengths, la_c, vc_c, r._table_x, r._table_y, F, g_ic, None,
+                                                 self.flat_grad[lo:lo + 7], self.flat_grad[hi - 4:hi - 3])
+        else:
+            g_raw_c = ops.composite_emission_bwd(raw_c, z, rays_d, g_ic.view(-1), None)
+        ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
+        h_coarse = self._reduce_async('coarse_model')
+        for h in (h_fine, h_coarse):
+            if h is not None:
+                h.wait()
+        # ---- optimiser (grads averaged over ranks == Lightning dp's mean of replica losses)
+        self.step_count += 1
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.scratch,
+                      self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
+        for name in ('fine_model', 'coarse_model'):   # packed bf16 weights must be refreshed next forward
+            getattr(r, name)._pack_key = None
+        if self.lr > 5e-5:                             # sunerf.py:36-40
+            self.lr *= self.gamma
+        return {'losses': losses, 'coarse_image': img_c, 'fine_image': img_f, 'grad_norm': self.grad_norm,
+                'z_vals_hierarchical': new_z}
+
+    def _reduce_async(self, name):
+        if self.world == 1:
+            return None
+        lo, hi = self.model_range[name]
+        return torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True)
+
+    def check_finite(self) -> None:
+        """The reference asserts on NaN/Inf every step (sunerf.py:105-107); here it is one device flag read on demand."""
+        if int(self.finite_flag.item()) != 0:
+            raise AssertionError('! [Numerical Alert] a rendered output contains NaN or Inf')

@@ -1,0 +1,127 @@
+/*
+ * sunerf_b200.h - C ABI of the B200-native SuNeRF ray-render hot path.
+ *
+ * The reference (FrontierDevelopmentLab/2024-HL-SPI3S-SuNeRF) has no FFI: its boundary is a Python class
+ * surface.  This header is what a ctypes binding on the reference side would load;
+ * each entry point cites the reference code it replaces (paths relative to the upstream tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch), unless it says "host";
+ *   - every entry is stream-ordered on `stream` (a cudaStream_t), never synchronises, keeps no
+ *     pointer after return, allocates nothing and is safe to call from several host threads;
+ *   - return value: 0 ok, <0 bad argument (SNF_E_*), >0 a cudaError_t;
+ *   - float32 everywhere unless a name says bf16; tensors are contiguous row-major.
+ */
+#ifndef SUNERF_B200_H
+#define SUNERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNF_VERSION 100
+#define SNF_E_ARG (-1)      /* null pointer / non-positive size */
+#define SNF_E_SHAPE (-2)    /* size outside what the kernels are instantiated for */
+#define SNF_E_ALIGN (-3)    /* pointer not aligned as documented */
+#define SNF_N_AIA 7         /* AIA channels 94,131,171,193,211,304,335 (model.py:154-162) */
+#define SNF_TABLE_LEN 101   /* logT grid of aia_temp_resp.genx */
+
+int snf_version(void);
+const char *snf_error_string(int code);
+/* number of kernel launches issued through this library by the calling process (bench.py gpu_launches) */
+int64_t snf_launch_count(void);
+
+/* ---- a1: StratifiedSampler.forward, sunerf/train/sampling.py:68-102 -------------------------------
+ * t_vals[S] is the sampler buffer (linspace(0,1,S)); t_rand[N,S] is the torch.rand draw of :97, or NULL
+ * for perturb=False.  Writes z_vals[N,S] and, if non-NULL, points[N,S,3].  Same fp32 operation order as
+ * the reference (no FMA contraction). */
+int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals, const float *t_rand,
+                          int64_t N, int S, float distance, float solar_R, float *z_vals, float *points,
+                          void *stream);
+
+/* ---- a2: HierarchicalSampler.forward + sample_pdf, sampling.py:111-169 (perturb=False) --------------
+ * z_vals[N,S], weights[N,S] (coarse weights), u[n_new] = linspace(0,1,n_new).
+ * cdf_in[N,S-1]: optional externally supplied CDF (stage-boundary parity test); NULL -> built here.
+ * Outputs: new_z[N,n_new], z_comb[N,S+n_new] (sorted merge); optional inds[N,n_new] (int64, the
+ * searchsorted(right=True) result) and cdf_out[N,S-1].  S<=256, n_new<=512. */
+int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in, int64_t N,
+                      int S, int n_new, float *new_z, float *z_comb, int64_t *inds, float *cdf_out, void *stream);
+
+/* ---- a3: query = cat(o + d*z, t), sunerf/rendering/base_tracing.py:64-65, 83-84; sampling.py:100 ---- */
+int snf_make_query(const float *rays_o, const float *rays_d, const float *z, const float *times, int64_t N, int S,
+                   float *query /*[N,S,4]*/, void *stream);
+
+/* ---- a4-a6: PositionalEncoding + NeRF / NeRF_DT forward, sunerf/model/model.py:44-57,123-132,169-187 -
+ * Network: enc(4->84) -> n_hidden x [Linear(.,d_filter)+sin] -> Linear(d_filter,2) (+ out_offset).
+ * W, B: HOST arrays of n_hidden+1 device pointers in nn.Linear layout (weight[out,in]).
+ * fp32 entry points: FFMA SIMT, the 1e-5 parity mode.  ws: workspace of snf_mlp_ws_bytes() bytes.
+ * train!=0 keeps every layer's activation and cosine in ws for snf_mlp_bwd_f32. */
+int64_t snf_mlp_ws_bytes(int64_t M, int n_hidden, int d_filter, int mode /*0 fp32, 1 bf16*/, int train);
+int snf_mlp_fwd_f32(const float *x /*[M,4]*/, int64_t M, const float *const *W, const float *const *B,
+                    int n_hidden, int d_filter, float out_offset0, float out_offset1, float *out /*[M,2]*/,
+                    void *ws, int train, void *stream);
+/* gW/gB: HOST arrays of device pointers, same shapes as W/B, OVERWRITTEN with the gradients. */
+int snf_mlp_bwd_f32(const float *x, int64_t M, const float *const *W, int n_hidden, int d_filter,
+                    const float *grad_out /*[M,2]*/, void *ws, float *const *gW, float *const *gB, void *stream);
+
+/* bf16 tensor-core entry points (tcgen05 + TMEM, weights streamed by TMA bulk copies).  d_filter==512,
+ * n_hidden==8 only.  `packed`: snf_mlp_pack_bytes() bytes holding the bf16 UMMA-layout copy of the weights;
+ * repack!=0 re-converts from W/B first (call with repack=1 whenever the fp32 weights changed). */
+int64_t snf_mlp_pack_bytes(void);
+int snf_mlp_pack_bf16(const float *const *W, const float *const *B, void *packed, void *stream);
+int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, float out_offset0, float out_offset1,
+                     float *out, void *ws, int train, void *stream);
+int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
+                     float *const *gW, float *const *gB, void *stream);
+
+/* ---- a7: SimpleStar.forward, sunerf/model/stellar_model.py:53-102 --------------------------------- */
+int snf_simple_star_fwd(const float *x /*[M,4]*/, int64_t M, float rho_0, float h0, float T0, float R_s,
+                        float t_photosphere, float *out /*[M,2]*/, void *stream);
+
+/* ---- a8: EmissionRadiativeTransfer.raw2outputs, sunerf/rendering/emission.py:14-54 ----------------
+ * + cumprod_exclusive, base_tracing.py:135-156.  image[N], weights[N,S], absorption[N,S].  S<=256. */
+int snf_composite_emission_fwd(const float *raw /*[N,S,2]*/, const float *z /*[N,S]*/, const float *rays_d,
+                               int64_t N, int S, float *image, float *weights, float *absorption, void *stream);
+/* analytic backward: g_image[N], g_absorption[N,S] (or NULL) -> g_raw[N,S,2] (overwritten) */
+int snf_composite_emission_bwd(const float *raw, const float *z, const float *rays_d, int64_t N, int S,
+                               const float *g_image, const float *g_absorption, float *g_raw, void *stream);
+
+/* ---- a9: DensityTemperatureRadiativeTransfer.raw2outputs, rendering/density_temperature.py:192-271 -
+ * wavelengths[N,C] float (0 = channel absent); log_abs[7], vol_c[1], table_x[101], table_y[7,101] device.
+ * image[N,C], weights[N,S], regq[N,S].  S<=256, C<=8. */
+int snf_composite_dt_fwd(const float *inferences /*[N,S,2]*/, const float *z, const float *wavelengths, int64_t N,
+                         int S, int C, const float *log_abs, const float *vol_c, const float *table_x,
+                         const float *table_y, float pixel_intensity_factor, float *image, float *weights,
+                         float *regq, void *stream);
+/* g_image[N,C], g_regq[N,S] (or NULL) -> g_inferences[N,S,2] (overwritten); g_log_abs[7] and g_vol_c[1]
+ * are ACCUMULATED into (caller zeroes them). */
+int snf_composite_dt_bwd(const float *inferences, const float *z, const float *wavelengths, int64_t N, int S, int C,
+                         const float *log_abs, const float *vol_c, const float *table_x, const float *table_y,
+                         float pixel_intensity_factor, const float *g_image, const float *g_regq,
+                         float *g_inferences, float *g_log_abs, float *g_vol_c, void *stream);
+
+/* ---- a10: SuNeRFRendering.forward epilogue, base_tracing.py:91-111; regularization :43-44 and
+ * density_temperature.py:273-274.  kind 0 = emission: reg = relu(dist-r0)*(1-q); 1 = DT: relu(dist-r0)*relu(q).
+ * g_q (optional, [N,S]): d(lambda*mean(reg))/dq for the backward of the fine compositing. */
+int snf_render_epilogue(const float *rays_o, const float *rays_d, const float *z_comb, const float *weights,
+                        const float *q, int64_t N, int S, float r0, int kind, float *height_map,
+                        float *absorption_map, float *reg, float reg_grad_scale, float *g_q, void *stream);
+
+/* ---- a11: training_step losses, sunerf/model/sunerf.py:98-131 (asinh-MSE, train/scaling.py:17-28) and
+ * :173-206 (plain MSE).  images [N,C]; losses[4] = {total, coarse, fine, reg}; g_coarse/g_fine [N,C];
+ * finite_flag[1] is OR-ed with 1 when any of the inputs is NaN/Inf (the assert of :105-107). */
+int snf_train_loss(const float *coarse, const float *fine, const float *target, const float *reg, int64_t N, int C,
+                   int64_t n_reg, int asinh_scaling, float asinh_a, float lambda_image, float lambda_reg,
+                   float *losses, float *g_coarse, float *g_fine, int *finite_flag, void *stream);
+
+/* ---- a12: clip-by-global-norm (run_emission.py:72) + Adam (sunerf.py:30-35) on one flat buffer ------
+ * grads are first scaled by grad_scale (1/world_size after the allreduce).  scratch: >= 1024 floats.
+ * step is 1-based.  norm_out[1] receives the pre-clip global norm. */
+int snf_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t step, float clip_norm, float grad_scale,
+                  float *scratch, float *norm_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,63 @@
+"""CPU suite: the C-ABI library builds for sm_100a without a GPU, loads, and exports exactly what include/*.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'sunerf_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(snf_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import sunerf_b200
+    path = sunerf_b200.build()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f'{n} declared in include/sunerf_b200.h but not exported'
+    assert set(names) == set(sunerf_b200._lib.EXPORTS), set(names) ^ set(sunerf_b200._lib.EXPORTS)
+    assert sunerf_b200._lib.lib().snf_version() == 100
+    assert sunerf_b200._lib.lib().snf_error_string(-2).decode().startswith('shape')
+
+
+def test_no_cpu_fallback():
+    import sunerf_b200
+    r = sunerf_b200.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'n_layers': 2, 'd_filter': 16})
+    with pytest.raises(sunerf_b200.SnfError):
+        r(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 1))
+    with pytest.raises(sunerf_b200.SnfError):
+        sunerf_b200.ops.stratified_sample(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(64), None, 1.3, 1.0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, '2024-hl-spi3s-sunerf_b200')
+    for f in os.listdir(pkg):
+        if f.endswith('.py'):
+            assert 'oracle' not in open(os.path.join(pkg, f)).read().replace('# oracle', ''), f
+
+
+def test_reference_surface():
+    import inspect
+    import sunerf_b200 as s
+    sig = inspect.signature(s.SuNeRFRendering.__init__)
+    assert list(sig.parameters)[1:] == ['Rs_per_ds', 'sampling_config', 'hierarchical_sampling_config', 'model', 'model_config']
+    sig = inspect.signature(s.DensityTemperatureRadiativeTransfer.__init__)
+    assert {'model_config', 'device', 'aia_exp_time', 'pixel_intensity_factor'} <= set(sig.parameters)
+    with pytest.raises(ValueError):
+        s.EmissionRadiativeTransfer(Rs_per_ds=1, sampling_config={'type': 'nope'})
+    with pytest.raises(ValueError):
+        s.EmissionRadiativeTransfer(Rs_per_ds=1, hierarchical_sampling_config={'type': 'nope'})
+    m = s.NeRF_DT()
+    keys = set(m.state_dict().keys())
+    assert {'in_layer.0.freq_bands', 'in_layer.1.weight', 'layers.6.bias', 'out_layer.weight', 'log_absortpion.94',
+            'log_absortpion.335', 'volumetric_constant'} <= keys
+    assert sum(p.numel() for p in s.NeRF().parameters()) == 1883138
