@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py - SuNeRF ray-render hot path on B200: train rays/s (fwd+bwd+optimiser) and render Msamples/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU PyTorch path (oracle port)
+
+Workload (BASELINE.json configs[1], `emission_2012_08-193.yaml`): emission SuNeRF, two 8x512 sine MLPs, 64 coarse +
+128 hierarchical samples per ray, 1024 synthetic rays per GPU per step, random-init weights.
+One "step" = one full training step: sampling, both field networks forward, compositing, asinh-MSE + regulariser
+loss, analytic backward into all 3.77 M parameters, (N>1: NCCL all-reduce of the flat gradient), clip + Adam.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 1024
+S_COARSE, S_FINE = 64, 192
+FLOP_FWD_POINT = 3758080          # 2*(84*512 + 7*512^2 + 512*2)          SURVEY.md section 8d
+FLOP_BWD_POINT = 7430144          # wgrad 9 layers + dgrad 8 layers
+FLOP_TRAIN_RAY = (S_COARSE + S_FINE) * (FLOP_FWD_POINT + FLOP_BWD_POINT)   # 2.8642e9
+FLOP_RENDER_RAY = (S_COARSE + S_FINE) * FLOP_FWD_POINT                     # 9.6207e8
+RENDER_BATCH = 4096               # render_mhd.yaml batch_size
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'tflops': d.get('bf16_tflops_sustained', 1400.0), 'tflops_burst': d.get('bf16_tflops', 1590.0),
+                'hbm': d.get('hbm_gbs', 6650.0), 'src': 'measured'}
+    return {'tflops': 1400.0, 'tflops_burst': 1590.0, 'hbm': 6650.0, 'src': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def synthetic_batch(n, seed):
+    """SURVEY.md section 8d synthetic rays: 1 AU observers, helioprojective pixel directions, t~U(0,30 d), target~U(0,1)."""
+    from sunerf_b200.rays import synthetic_rays
+    return synthetic_rays(n, seed=seed, H=256, W=256, plate_arcsec=9.4, t_days=30.0)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU PyTorch path for the same step (oracle port: same ATen ops as the reference, which
+    cannot travel to the GPU box), all host threads, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import sunerf_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.ref_rays
+    b = synthetic_batch(n, seed=0)
+    torch.manual_seed(7)
+    pc, pf = orc.FieldParams.init(1).requires_grad_(), orc.FieldParams.init(2).requires_grad_()
+    opt = orc.AdamState(pc.tensors() + pf.tensors())
+    cfg = orc.RenderConfig(kind='emission')
+    gen = torch.Generator().manual_seed(3)
+
+    def step():
+        t_rand = torch.rand(n, 64, generator=gen)
+        return orc.train_step(cfg, pc, pf, opt, b['rays_o'], b['rays_d'], b['times'], b['target'], None, t_rand)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {'metric': 'train_rays_per_s', 'value': v, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{n} rays/step (of {RAYS_PER_GPU}) x {args.steps} steps, torch CPU fp32'},
+            'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(gpus):
+    return {'workload': 'emission_2012_08-193.yaml: emission SuNeRF train step, 2 x (84->512x8->2) sine MLP, 64+128 samples/ray',
+            'rays_per_gpu': RAYS_PER_GPU, 'global_rays': RAYS_PER_GPU * gpus, 'samples_per_ray': S_COARSE + S_FINE,
+            'parallelism': f'ray-shard dp{gpus}, one NCCL all-reduce of the flat fp32 gradient per step',
+            'l2': 'per-step working set (saved layer activations, >1 GB) exceeds the 126 MB L2; no explicit flush'}
+
+
+def cpu_baseline(sample_rays=256):
+    from oracle import sunerf_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = synthetic_batch(sample_rays, seed=0)
+    pc, pf = orc.FieldParams.init(1).requires_grad_(), orc.FieldParams.init(2).requires_grad_()
+    opt = orc.AdamState(pc.tensors() + pf.tensors())
+    cfg = orc.RenderConfig(kind='emission')
+    gen = torch.Generator().manual_seed(3)
+    best = None
+    for i in range(3):   # 1 warm-up + best of 2
+        t_rand = torch.rand(sample_rays, 64, generator=gen)
+        t0 = time.perf_counter()
+        orc.train_step(cfg, pc, pf, opt, b['rays_o'], b['rays_d'], b['times'], b['target'], None, t_rand)
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return {'value': sample_rays / best, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+            'sample': f'1 warm-up + best of 2 full train steps on {sample_rays} of the {RAYS_PER_GPU} rays, torch CPU fp32 oracle'}
+
+
+# ------------------------------------------------------------------------------------------ this repo's arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--ref-rays', type=int, default=128)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    import sunerf_b200 as s
+    from sunerf_b200 import ops
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    pk = peaks()
+
+    torch.manual_seed(7)                      # run_density_temperature.py:17; same init on every rank (no broadcast)
+    rend = s.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'precision': args.precision}).to(dev)
+    trainer = s.RayTrainer(rend)
+    N = RAYS_PER_GPU
+    b = synthetic_batch(N * world, seed=0)    # global batch, sharded by rank: rank r owns rays [r*N, (r+1)*N)
+    host = {k: v[rank * N:(rank + 1) * N].contiguous().pin_memory() for k, v in b.items()}
+    devb = {k: v.to(dev) for k, v in host.items()}
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+
+    # ---- CUDA-event instrumentation of the dominant kernel group (field-network forward + backward)
+    mlp_events = []
+    _fwd, _bwd = ops.mlp_forward, ops.mlp_backward
+
+    def timed(fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(*a, **k); e1.record()
+            mlp_events.append((e0, e1))
+            return r
+        return w
+    ops.mlp_forward, ops.mlp_backward = timed(_fwd), timed(_bwd)
+
+    def step_resident():
+        t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
+        return trainer.step(devb['rays_o'], devb['rays_d'], devb['times'], devb['target'], t_rand=t_rand)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
+        res = trainer.step(d['rays_o'], d['rays_d'], d['times'], d['target'], t_rand=t_rand)
+        return res['losses'].cpu()          # device->host read of the step's result (synchronises)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    mlp_events.clear()
+    l0 = ops.launch_count()
+    ms = timed_loop(step_resident, args.steps)
+    launches = ops.launch_count() - l0
+    mlp_ms = sum(a.elapsed_time(bb) for a, bb in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
+    ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_loop(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    trainer.check_finite()
+
+    # ---- forward-only render throughput (render_mhd.yaml batch of 4096 rays, hierarchical sampling on)
+    rb = synthetic_batch(RENDER_BATCH, seed=1)
+    rdev = {k: v.to(dev) for k, v in rb.items()}
+
+    def render_once():
+        with torch.no_grad():
+            return rend(rdev['rays_o'], rdev['rays_d'], rdev['times'])
+    for _ in range(3):
+        render_once()
+    ms_render = timed_loop(render_once, max(3, args.steps // 2)) / max(3, args.steps // 2)
+
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    value = N * world * args.steps / (ms * 1e-3)
+    e2e = N * world * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    achieved = N * FLOP_TRAIN_RAY / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': workload_config(world),
+            'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches) * world,
+            'roofline': {'bound': 'tensor', 'kernel': f'field-network MLP forward+backward ({args.precision})',
+                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                         'traffic': None, 'peak_source': pk['src'] + ' (sustained cuBLAS bf16)',
+                         'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / (ms / args.steps),
+                         'algorithmic_flop_per_step': N * FLOP_TRAIN_RAY},
+            'render': {'metric': 'render_Msamples_per_s', 'value': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_render * 1e-3) / 1e6,
+                       'unit': 'Msamples/s', 'rays_per_batch': RENDER_BATCH, 'ms_per_batch': ms_render,
+                       'tensor_frac': RENDER_BATCH * FLOP_RENDER_RAY / (ms_render * 1e-3) / 1e12 / pk['tflops']},
+            'clocks': clk}
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()
