@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
 }
 
 struct Bf16Ws {
-  uint8_t *enc, *h, *c;
+  uint8_t *enc, *h, *c, *d;
   int64_t bytes;
 };
 inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
@@ -319,6 +319,7 @@ inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
     w.enc = p + off; off += tiles * 2 * SLAB_BYTES;
     w.h = p + off; off += tiles * NH * (int64_t)A_BYTES;
     w.c = p + off; off += tiles * NH * (int64_t)A_BYTES;
+    w.d = p + off; off += tiles * NH * (int64_t)A_BYTES;   // dpre_l images written by the backward
   }
   w.bytes = off > 0 ? off : 256;
   return w;
@@ -331,7 +332,13 @@ using namespace snf;
 
 int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train) { return bf::bf16_layout(nullptr, M, train).bytes; }
 
-extern "C" int64_t snf_mlp_pack_bytes(void) { return bf::PACK_BYTES; }
+// snf_mlp_bf16_bwd.cu
+int64_t snf_bf16_pack_total_bytes();
+int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st);
+int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, uint8_t *enc, uint8_t *h, uint8_t *c, uint8_t *d,
+                      float *const *gW, float *const *gB, int num_sms, cudaStream_t st);
+
+extern "C" int64_t snf_mlp_pack_bytes(void) { return snf_bf16_pack_total_bytes(); }
 
 extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, void *packed, void *stream) {
   SNF_CHECK_PTR(W); SNF_CHECK_PTR(B); SNF_CHECK_PTR(packed); SNF_CHECK_ALIGN(packed, 1024);
@@ -344,7 +351,7 @@ extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, v
   bf::pack_small_kernel<<<(nsmall + 255) / 256, 256, 0, st>>>(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], W[8], B[8],
                                                              reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_W_BYTES));
   count_launch(2);
-  return launch_status();
+  return snf_bf16_pack_wt(W, packed, st);   // W^T blocks for the dgrad chain
 }
 
 static int g_num_sms = 0;
@@ -390,6 +397,11 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
 
 extern "C" int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
                                 float *const *gW, float *const *gB, void *stream) {
-  (void)x; (void)M; (void)packed; (void)grad_out; (void)ws; (void)gW; (void)gB; (void)stream;
-  return SNF_E_SHAPE;   // implemented in the next milestone
+  (void)x;
+  SNF_CHECK_PTR(packed); SNF_CHECK_PTR(grad_out); SNF_CHECK_PTR(ws); SNF_CHECK_PTR(gW); SNF_CHECK_PTR(gB);
+  SNF_CHECK_ALIGN(grad_out, 8); SNF_CHECK_ALIGN(ws, 1024); SNF_CHECK_ALIGN(packed, 1024);
+  if (M <= 0) return SNF_E_ARG;
+  for (int l = 0; l <= bf::NH; ++l) { SNF_CHECK_PTR(gW[l]); SNF_CHECK_PTR(gB[l]); SNF_CHECK_ALIGN(gW[l], 16); }
+  bf::Bf16Ws w = bf::bf16_layout(ws, M, 1);
+  return snf_bf16_backward(grad_out, M, packed, w.enc, w.h, w.c, w.d, gW, gB, num_sms(), (cudaStream_t)stream);
 }

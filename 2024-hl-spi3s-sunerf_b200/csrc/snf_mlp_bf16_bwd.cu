@@ -1,0 +1,467 @@
+// bf16 tensor-core backward of the field network (sm_100a).  Two persistent warp-specialised kernels over the
+// tile images the forward saved (snf_mlp_bf16.cu: enc, H_l = sin(pre_l), C_l = cos(pre_l), all [tile][..][128 x 512]
+// bf16 in the UMMA K-major SWIZZLE_128B image):
+//
+//  dgrad chain  (mlp_dgrad_bf16_kernel): per 128-point tile, dpre_7 = (g W_out) * C_7 in the epilogue warps, then for
+//     l = 7..1:  dpre_{l-1} = (dpre_l W_l) * C_{l-1}  -- tcgen05.mma with A = dpre_l image in shared memory, B = W_l^T
+//     blocks streamed by TMA, D in TMEM; every dpre_l image is bulk-stored to HBM (D_l) for the weight gradients.
+//  wgrad        (mlp_wgrad_bf16_kernel): dW_l[o,i] = sum_p D_l[p,o] Hprev_l[p,i].  The saved images are read
+//     "transposed" as MN-major UMMA operands (same bytes, different descriptor), 32 points per pipeline stage;
+//     a CTA owns a 128(o) x 512(i) fp32 accumulator (all of TMEM) for a range of tiles, then flushes it with
+//     red.global.add.v4.f32 into the flat gradient buffer.  The otherwise idle epilogue warps sum the D_l stages
+//     over points for the bias gradients.
+//
+// This is what torch.autograd derives for NeRF.forward (sunerf/model/model.py:44-57) - restated analytically.
+#include "snf_common.cuh"
+#include "snf_tcgen05.cuh"
+
+namespace snf {
+namespace bf {
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int D = 512;
+constexpr int NH = 8;
+constexpr int SLAB_BYTES = TILE_M * 128;
+constexpr int A_BYTES = 8 * SLAB_BYTES;
+constexpr int WBLK_BYTES = 256 * 128;
+constexpr int NSTAGE = 3;
+constexpr int NTHREADS = 192;
+constexpr int SMEM_BYTES = A_BYTES + NSTAGE * WBLK_BYTES + 1024 + 256;
+constexpr int WT_BLOCKS = 7 * 16;                        // layers 1..7, 2 n-halves x 8 k-slabs
+constexpr int64_t PACK_W_BYTES = (int64_t)(4 + 7 * 16) * WBLK_BYTES;          // forward image (snf_mlp_bf16.cu)
+constexpr int64_t PACK_SMALL_BYTES = (NH * D + 2 * D + 4) * 4;
+constexpr int64_t PACK_WT_OFF = (PACK_W_BYTES + PACK_SMALL_BYTES + 1023) / 1024 * 1024;
+constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+
+// ------------------------------------------------------------------------------------------ W^T packing
+// block (l, nh, ks): rows = input feature i (256 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
+__global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const float *w2, const float *w3, const float *w4,
+                                                      const float *w5, const float *w6, const float *w7,
+                                                      uint4 *__restrict__ dst) {
+  const float *W[7] = {w1, w2, w3, w4, w5, w6, w7};
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)WT_BLOCKS * (WBLK_BYTES / 16)) return;
+  const int blk = (int)(idx / (WBLK_BYTES / 16)), within = (int)(idx % (WBLK_BYTES / 16));
+  const int li = blk / 16, nh = (blk % 16) >> 3, ks = blk & 7;
+  const int r = within >> 3, pos = within & 7, c8 = pos ^ (r & 7);
+  const int i = nh * 256 + r, o0 = ks * 64 + c8 * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = W[li][(o0 + j) * D + i];
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  dst[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
+}
+
+// ------------------------------------------------------------------------------------------ dgrad chain
+struct DgradParams {
+  const float2 *g;          // [M] dL/d out
+  int64_t M;
+  int num_tiles;
+  const uint8_t *packed;    // forward pack + W^T blocks
+  const uint8_t *save_c;    // [tiles][8][128 KB]
+  uint8_t *save_d;          // [tiles][8][128 KB]  dpre_l images (output)
+};
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sW = base + A_BYTES, sBar = sW + NSTAGE * WBLK_BYTES;
+  uint8_t *gA = smem_raw + (base - smem_u32(smem_raw));
+  auto bar_full = [&](int s) { return sBar + 8u * s; };
+  auto bar_empty = [&](int s) { return sBar + 8u * (NSTAGE + s); };
+  const uint32_t bar_acc = sBar + 8u * (2 * NSTAGE), bar_aready = sBar + 8u * (2 * NSTAGE + 1);
+  const uint32_t tmem_slot = sBar + 8u * (2 * NSTAGE + 2);
+  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(gA + A_BYTES + NSTAGE * WBLK_BYTES + 8 * (2 * NSTAGE + 2));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_aready, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot_g;
+  const uint8_t *wt = p.packed + PACK_WT_OFF;
+  const float *w_out = reinterpret_cast<const float *>(p.packed + PACK_W_BYTES) + NH * D;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+        for (int l = NH - 1; l >= 1; --l)
+          for (int b = 0; b < 16; ++b) {
+            mbar_wait(bar_empty(s), ph ^ 1);
+            mbar_arrive_expect_tx(bar_full(s), WBLK_BYTES);
+            bulk_g2s(sW + s * WBLK_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES, WBLK_BYTES, bar_full(s));
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, 256);
+      int s = 0; uint32_t ph = 0, ph_a = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+        for (int l = NH - 1; l >= 1; --l) {
+          mbar_wait(bar_aready, ph_a); ph_a ^= 1;
+          tcgen05_fence_after();
+          for (int nh = 0; nh < 2; ++nh)
+            for (int ks = 0; ks < 8; ++ks) {
+              mbar_wait(bar_full(s), ph);
+              tcgen05_fence_after();
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
+                const uint64_t bd = smem_desc(sW + s * WBLK_BYTES + k4 * 32, 16, 1024);
+                mma_ss(tmem + nh * 256, ad, bd, idesc, (ks | k4) != 0);
+              }
+              mma_commit(bar_empty(s));
+              if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            }
+          mma_commit(bar_acc);
+        }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 64;
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t ph_acc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t m = (int64_t)tile * TILE_M + row;
+      const uint8_t *c_tile = p.save_c + (int64_t)tile * NH * A_BYTES;
+      uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
+      // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos_7
+      {
+        if (et == 0) bulk_wait_read_all();
+        named_bar_sync(1, 128);
+        float2 gg = make_float2(0.f, 0.f);
+        if (m < p.M) gg = p.g[m];
+        const uint8_t *c7 = c_tile + (int64_t)(NH - 1) * A_BYTES;
+#pragma unroll 1
+        for (int c = 0; c < D / 8; ++c) {       // 64 chunks of 8 columns
+          const uint32_t off = (c >> 3) * SLAB_BYTES + sw128_chunk_off(row, c & 7);
+          const uint4 cv = *reinterpret_cast<const uint4 *>(c7 + off);
+          const float4 wa0 = __ldg(reinterpret_cast<const float4 *>(w_out + c * 8)), wa1 = __ldg(reinterpret_cast<const float4 *>(w_out + c * 8 + 4));
+          const float4 wb0 = __ldg(reinterpret_cast<const float4 *>(w_out + D + c * 8)), wb1 = __ldg(reinterpret_cast<const float4 *>(w_out + D + c * 8 + 4));
+          uint4 o;
+          o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * bf_lo(cv.x), (gg.x * wa0.y + gg.y * wb0.y) * bf_hi(cv.x));
+          o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * bf_lo(cv.y), (gg.x * wa0.w + gg.y * wb0.w) * bf_hi(cv.y));
+          o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * bf_lo(cv.z), (gg.x * wa1.y + gg.y * wb1.y) * bf_hi(cv.z));
+          o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * bf_lo(cv.w), (gg.x * wa1.w + gg.y * wb1.w) * bf_hi(cv.w));
+          *reinterpret_cast<uint4 *>(gA + off) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          uint8_t *dst = d_tile + (int64_t)(NH - 1) * A_BYTES;
+#pragma unroll 1
+          for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
+          bulk_commit();
+        }
+        tcgen05_fence_before();
+        mbar_arrive(bar_aready);
+      }
+      for (int l = NH - 1; l >= 1; --l) {
+        // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos_{l-1} -> dpre_{l-1}
+        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+        tcgen05_fence_after();
+        if (et == 0) bulk_wait_read_all();
+        named_bar_sync(1, 128);
+        const uint8_t *cprev = c_tile + (int64_t)(l - 1) * A_BYTES;
+#pragma unroll 1
+        for (int g = 0; g < D / 32; ++g) {
+          uint4 cv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            cv[c] = *reinterpret_cast<const uint4 *>(cprev + (g >> 1) * SLAB_BYTES + sw128_chunk_off(row, (g & 1) * 4 + c));
+          uint32_t acc[32];
+          tmem_ld32(tm_row + g * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (g >> 1) * SLAB_BYTES + sw128_chunk_off(row, (g & 1) * 4 + c);
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * bf_lo(cv[c].x), __uint_as_float(acc[c * 8 + 1]) * bf_hi(cv[c].x));
+            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * bf_lo(cv[c].y), __uint_as_float(acc[c * 8 + 3]) * bf_hi(cv[c].y));
+            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * bf_lo(cv[c].z), __uint_as_float(acc[c * 8 + 5]) * bf_hi(cv[c].z));
+            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * bf_lo(cv[c].w), __uint_as_float(acc[c * 8 + 7]) * bf_hi(cv[c].w));
+            *reinterpret_cast<uint4 *>(gA + off) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          uint8_t *dst = d_tile + (int64_t)(l - 1) * A_BYTES;
+#pragma unroll 1
+          for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
+          bulk_commit();
+        }
+        if (l > 1) {
+          tcgen05_fence_before();
+          mbar_arrive(bar_aready);
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+constexpr int WG_KSTAGE = 32;                           // points per pipeline stage
+constexpr int WG_SLAB_STAGE = WG_KSTAGE * 128;          // 4 KB: 32 rows of one 64-feature slab
+constexpr int WG_STAGE_BYTES = 10 * WG_SLAB_STAGE;      // 2 (o-block) + 8 (all i) slabs = 40 KB
+constexpr int WG_NSTAGE = 5;
+constexpr int WG_SMEM_BYTES = WG_NSTAGE * WG_STAGE_BYTES + 1024 + 256;
+
+struct WgradParams {
+  const uint8_t *save_d, *save_h, *save_enc;
+  int num_tiles, tiles_per_item, num_items;
+  float *gW[NH];
+  float *gB[NH];
+};
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_wgrad_bf16_kernel(const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gS = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sBar = base + WG_NSTAGE * WG_STAGE_BYTES;
+  auto bar_full = [&](int s) { return sBar + 8u * s; };
+  auto bar_empty = [&](int s) { return sBar + 8u * (WG_NSTAGE + s); };
+  const uint32_t bar_acc = sBar + 8u * (2 * WG_NSTAGE), bar_accfree = sBar + 8u * (2 * WG_NSTAGE + 1);
+  const uint32_t tmem_slot = sBar + 8u * (2 * WG_NSTAGE + 2);
+  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(gS + WG_NSTAGE * WG_STAGE_BYTES + 8 * (2 * WG_NSTAGE + 2));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 4); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfree, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot_g;
+
+  // item -> (tile range, layer, o-block); the 4 o-blocks of one (range, layer) are adjacent so that CTAs running
+  // side by side share the Hprev tiles in L2
+  auto decode = [&](int item, int &l, int &ob, int &t0, int &t1) {
+    ob = item & 3; l = (item >> 2) & 7;
+    const int r = item >> 5;
+    t0 = r * p.tiles_per_item;
+    t1 = min(t0 + p.tiles_per_item, p.num_tiles);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int l, ob, t0, t1; decode(item, l, ob, t0, t1);
+        const int nb = l == 0 ? 2 : 8;
+        for (int t = t0; t < t1; ++t) {
+          const uint8_t *dimg = p.save_d + ((int64_t)t * NH + l) * A_BYTES + (int64_t)ob * 2 * SLAB_BYTES;
+          const uint8_t *himg = l == 0 ? p.save_enc + (int64_t)t * 2 * SLAB_BYTES
+                                       : p.save_h + ((int64_t)t * NH + (l - 1)) * A_BYTES;
+          for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
+            mbar_wait(bar_empty(s), ph ^ 1);
+            mbar_arrive_expect_tx(bar_full(s), (2 + nb) * WG_SLAB_STAGE);
+            const uint32_t st = base + s * WG_STAGE_BYTES;
+            for (int j = 0; j < 2; ++j)
+              bulk_g2s(st + j * WG_SLAB_STAGE, dimg + j * SLAB_BYTES + qd * WG_SLAB_STAGE, WG_SLAB_STAGE, bar_full(s));
+            for (int j = 0; j < nb; ++j)
+              bulk_g2s(st + (2 + j) * WG_SLAB_STAGE, himg + j * SLAB_BYTES + qd * WG_SLAB_STAGE, WG_SLAB_STAGE, bar_full(s));
+            if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc256 = idesc_bf16(128, 256, 1, 1), idesc128 = idesc_bf16(128, 128, 1, 1);
+      int s = 0; uint32_t ph = 0, ph_free = 0;
+      bool first_item = true;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int l, ob, t0, t1; decode(item, l, ob, t0, t1);
+        if (!first_item) { mbar_wait(bar_accfree, ph_free); ph_free ^= 1; tcgen05_fence_after(); }
+        first_item = false;
+        uint32_t accumulate = 0;
+        for (int t = t0; t < t1; ++t)
+          for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
+            mbar_wait(bar_full(s), ph);
+            tcgen05_fence_after();
+            const uint32_t st = base + s * WG_STAGE_BYTES;
+#pragma unroll
+            for (int k16 = 0; k16 < WG_KSTAGE / 16; ++k16) {
+              // MN-major operands: LBO = stride between 64-feature slabs inside the stage, SBO = 8-point groups
+              const uint64_t ad = smem_desc(st + k16 * 2048, WG_SLAB_STAGE, 1024);
+              if (l == 0) {
+                const uint64_t bd = smem_desc(st + 2 * WG_SLAB_STAGE + k16 * 2048, WG_SLAB_STAGE, 1024);
+                mma_ss(tmem, ad, bd, idesc128, accumulate);
+              } else {
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {
+                  const uint64_t bd = smem_desc(st + (2 + nh * 4) * WG_SLAB_STAGE + k16 * 2048, WG_SLAB_STAGE, 1024);
+                  mma_ss(tmem + nh * 256, ad, bd, idesc256, accumulate);
+                }
+              }
+              accumulate = 1;
+            }
+            mma_commit(bar_empty(s));
+            if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
+          }
+        mma_commit(bar_acc);
+      }
+    }
+  } else {
+    // bias-gradient partial sums while the pipeline runs, accumulator flush at the end of each item
+    const int q = warp & 3, et = threadIdx.x - 64;      // thread <-> output feature o = ob*128 + row
+    const int row = q * 32 + lane;
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
+    int s = 0; uint32_t ph = 0, ph_acc = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int l, ob, t0, t1; decode(item, l, ob, t0, t1);
+      float bsum = 0.f;
+      // column `row` of the D stage: slab row>>6, element row&63 of each of the 32 point-lines
+      const int bslab = row >> 6, bc8 = (row & 63) >> 3, be = row & 7;
+      for (int t = t0; t < t1; ++t)
+        for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
+          mbar_wait(bar_full(s), ph);
+          const uint8_t *st = gS + s * WG_STAGE_BYTES + bslab * WG_SLAB_STAGE;
+#pragma unroll 8
+          for (int r = 0; r < WG_KSTAGE; ++r) {
+            const uint16_t v = *reinterpret_cast<const uint16_t *>(st + sw128_chunk_off(r, bc8) + be * 2);
+            bsum += __uint_as_float((uint32_t)v << 16);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty(s));
+          if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
+        }
+      (void)et;
+      atomicAdd(p.gB[l] + ob * 128 + row, bsum);
+      // ---- flush dW_l[ob*128 + row, :]
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tcgen05_fence_after();
+      const int ncols = l == 0 ? 128 : D;
+      const int ld = l == 0 ? 84 : D;
+      float *wrow = p.gW[l] + (int64_t)(ob * 128 + row) * ld;
+#pragma unroll 1
+      for (int g = 0; g < ncols / 32; ++g) {
+        uint32_t acc[32];
+        tmem_ld32(tm_row + g * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          int col = g * 32 + i;
+          if (l == 0) {
+            if (col >= 88) continue;          // zero padding of the encoder image
+            if (col >= 84) col -= 84;         // residual columns fold back onto the raw-coordinate weights
+          }
+          red_add_v4(wrow + col, __uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                     __uint_as_float(acc[i + 3]));
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_accfree);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ output layer grads
+// gW_out[o,:] += sum_p g[p,o] h_7[p,:] ; gb_out[o] += sum_p g[p,o].  One CTA per group of tiles, thread <-> 4 columns.
+__global__ void __launch_bounds__(128) out_wgrad_bf16_kernel(const float2 *__restrict__ g, int64_t M, int num_tiles,
+                                                             int tiles_per_cta, const uint8_t *__restrict__ save_h,
+                                                             float *__restrict__ gW, float *__restrict__ gB) {
+  const int t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, num_tiles);
+  const int c0 = threadIdx.x * 4;                  // columns c0..c0+3 : slab c0>>6, chunk (c0&63)>>3, half (c0&7)>>2
+  float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, s0 = 0.f, s1 = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const uint8_t *h7 = save_h + ((int64_t)t * NH + (NH - 1)) * A_BYTES + (c0 >> 6) * SLAB_BYTES;
+    for (int r = 0; r < TILE_M; ++r) {
+      const int64_t m = (int64_t)t * TILE_M + r;
+      if (m >= M) break;
+      const float2 gg = g[m];
+      const uint2 hv = *reinterpret_cast<const uint2 *>(h7 + sw128_chunk_off(r, (c0 & 63) >> 3) + (c0 & 7) * 2);
+      const float h[4] = {bf_lo(hv.x), bf_hi(hv.x), bf_lo(hv.y), bf_hi(hv.y)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a0[j] += gg.x * h[j]; a1[j] += gg.y * h[j]; }
+      if (threadIdx.x == 0) { s0 += gg.x; s1 += gg.y; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { atomicAdd(gW + c0 + j, a0[j]); atomicAdd(gW + D + c0 + j, a1[j]); }
+  if (threadIdx.x == 0) { atomicAdd(gB, s0); atomicAdd(gB + 1, s1); }
+}
+
+}  // namespace bf
+}  // namespace snf
+
+using namespace snf;
+
+int64_t snf_bf16_pack_total_bytes() { return bf::PACK_TOTAL_BYTES; }
+
+int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
+  const int64_t chunks = (int64_t)bf::WT_BLOCKS * (bf::WBLK_BYTES / 16);
+  bf::pack_wt_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(
+      W[1], W[2], W[3], W[4], W[5], W[6], W[7], reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_WT_OFF));
+  count_launch();
+  return launch_status();
+}
+
+// ws layout (shared with snf_mlp_bf16.cu): [enc][H][C][D]
+int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, uint8_t *enc, uint8_t *h, uint8_t *c, uint8_t *d,
+                      float *const *gW, float *const *gB, int num_sms, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bf::mlp_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::WG_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
+  // gradients are accumulated with atomics: clear them first (ABI: overwritten)
+  const int64_t wsz[9] = {512 * 84, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 2 * 512};
+  for (int l = 0; l <= bf::NH; ++l) {
+    cudaMemsetAsync(gW[l], 0, wsz[l] * 4, st);
+    cudaMemsetAsync(gB[l], 0, (l < bf::NH ? 512 : 2) * 4, st);
+  }
+  bf::DgradParams dp{};
+  dp.g = reinterpret_cast<const float2 *>(grad_out);
+  dp.M = M; dp.num_tiles = num_tiles;
+  dp.packed = reinterpret_cast<const uint8_t *>(packed);
+  dp.save_c = c; dp.save_d = d;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(dp);
+
+  bf::WgradParams wp{};
+  wp.save_d = d; wp.save_h = h; wp.save_enc = enc;
+  wp.num_tiles = num_tiles;
+  int tpi = (num_tiles * 32 + 1023) / 1024;
+  if (tpi < 4) tpi = 4;
+  wp.tiles_per_item = tpi;
+  wp.num_items = ((num_tiles + tpi - 1) / tpi) * 32;
+  for (int l = 0; l < bf::NH; ++l) { wp.gW[l] = gW[l]; wp.gB[l] = gB[l]; }
+  const int wgrid = wp.num_items < num_sms ? wp.num_items : num_sms;
+  bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::NTHREADS, bf::WG_SMEM_BYTES, st>>>(wp);
+
+  const int tpc = (num_tiles + 4 * num_sms - 1) / (4 * num_sms);
+  bf::out_wgrad_bf16_kernel<<<(num_tiles + tpc - 1) / tpc, 128, 0, st>>>(dp.g, M, num_tiles, tpc, h, gW[bf::NH], gB[bf::NH]);
+  count_launch(3);
+  return launch_status();
+}

@@ -119,6 +119,8 @@ def mlp_forward(x, weights, biases, out_offsets=(0.0, 0.0), mode: str = 'fp32', 
     out = torch.empty(M, 2, device=x.device, dtype=torch.float32)
     ws = MLPWorkspace(M, n_hidden, d, mode, train, x.device)
     L = _lib.lib()
+    if M == 0:
+        return out, ws
     if mode == 'fp32':
         wl = [_f32(w, 'W') for w in weights]
         bl = [_f32(b, 'b') for b in biases]
