@@ -301,6 +301,52 @@ def test_emission_training_gradients_autograd():
     _grad_checks(g, 'fine_model', r.fine_model)
 
 
+def test_emission_training_gradients_bf16():
+    """bf16 tensor-core mode (tcgen05 forward, dgrad chain and MN-major wgrad): loss within 1e-2, per-parameter
+    gradient tensors within 5e-2 of the fp32 reference gradients (bf16 operands carry 2^-9 relative rounding)."""
+    import sunerf_b200 as s
+    g, r = _emission_module('bf16')
+    out = r(t(g['rays_o']), t(g['rays_d']), t(g['times']), t_rand=t(g['t_rand']))
+    scal = s.ImageAsinhScaling().cuda()
+    mse = torch.nn.MSELoss()
+    tgt = scal(t(g['target']))
+    loss = mse(scal(out['coarse_image']), tgt) + mse(scal(out['fine_image']), tgt) + out['regularization'].mean()
+    assert abs(loss.item() - float(g['loss'])) <= INT_TOL_BF16 * abs(float(g['loss']))
+    loss.backward()
+    from oracle.make_golden import GRAD_SLICES
+    worst = 0.0
+    for prefix, model in (('coarse_model', r.coarse_model), ('fine_model', r.fine_model)):
+        for name, p in model.named_parameters():
+            key = f'{prefix}.{name}'
+            ref = float(g[key + '.gnorm'])
+            got = p.grad.double().norm().item()
+            assert abs(got - ref) <= 5e-2 * ref, (key, got, ref)
+            if key + '.gslice' in g.files:
+                sl, rs = p.grad[GRAD_SLICES[name]].cpu(), torch.from_numpy(g[key + '.gslice'])
+                e = ((sl - rs).norm() / rs.norm()).item()
+                worst = max(worst, e)
+                assert e <= 5e-2, (key, e)
+    print('bf16 worst gradient-slice relative error', worst)
+
+
+def test_ray_trainer_bf16_matches_fp32():
+    import sunerf_b200 as s
+    g, r32 = _emission_module('fp32')
+    _, r16 = _emission_module('bf16')
+    t32, t16 = s.RayTrainer(r32), s.RayTrainer(r16)
+    args = (t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['target']))
+    a = t32.step(*args, t_rand=t(g['t_rand']))
+    b = t16.step(*args, t_rand=t(g['t_rand']))
+    assert abs(a['losses'][0].item() - b['losses'][0].item()) <= INT_TOL_BF16 * abs(a['losses'][0].item())
+    assert abs(a['grad_norm'].item() - b['grad_norm'].item()) <= 5e-2 * a['grad_norm'].item()
+    cos = torch.nn.functional.cosine_similarity(t32.flat_grad.double(), t16.flat_grad.double(), dim=0).item()
+    assert cos > 0.998, cos
+    # a second step runs on refreshed packed weights
+    b2 = t16.step(*args, t_rand=t(g['t_rand']))
+    assert torch.isfinite(b2['losses']).all()
+    t16.check_finite()
+
+
 def test_dt_training_gradients_autograd():
     import sunerf_b200 as s
     g, a, N = _dt_inputs()
@@ -342,9 +388,8 @@ def test_ray_trainer_matches_oracle_step():
     assert abs(res['grad_norm'].item() - lo['grad_norm']) <= GRAD_TOL * lo['grad_norm']
     w_new = r.fine_model.layers[3].weight.detach().cpu()
     ref_new = pf.weights[4].detach()
-    # first Adam step moves each weight by ~lr*sign(g); compare the updates, not the weights
-    g0 = golden('emission_render.npz')
-    assert (w_new - ref_new).abs().max() <= 2e-5
+    # the first Adam step moves every weight by ~lr*sign(g): an element whose gradient is ~0 may flip sign
+    assert (w_new - ref_new).abs().max() <= 2.1e-4
     frac_same = ((w_new - ref_new).abs() <= 2e-6).float().mean().item()
     assert frac_same > 0.98, frac_same
 
