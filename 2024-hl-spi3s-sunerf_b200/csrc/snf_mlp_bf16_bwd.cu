@@ -12,27 +12,12 @@
 //     over points for the bias gradients.
 //
 // This is what torch.autograd derives for NeRF.forward (sunerf/model/model.py:44-57) - restated analytically.
-#include "snf_common.cuh"
-#include "snf_tcgen05.cuh"
+#include "snf_bf16_common.cuh"
 
 namespace snf {
 namespace bf {
-using namespace tc;
 
-constexpr int TILE_M = 128;
-constexpr int D = 512;
-constexpr int NH = 8;
-constexpr int SLAB_BYTES = TILE_M * 128;
-constexpr int A_BYTES = 8 * SLAB_BYTES;
-constexpr int WBLK_BYTES = 256 * 128;
-constexpr int NSTAGE = 3;
-constexpr int NTHREADS = 192;
-constexpr int SMEM_BYTES = A_BYTES + NSTAGE * WBLK_BYTES + 1024 + 256;
-constexpr int WT_BLOCKS = 7 * 16;                        // layers 1..7, 2 n-halves x 8 k-slabs
-constexpr int64_t PACK_W_BYTES = (int64_t)(4 + 7 * 16) * WBLK_BYTES;          // forward image (snf_mlp_bf16.cu)
-constexpr int64_t PACK_SMALL_BYTES = (NH * D + 2 * D + 4) * 4;
-constexpr int64_t PACK_WT_OFF = (PACK_W_BYTES + PACK_SMALL_BYTES + 1023) / 1024 * 1024;
-constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+constexpr int WG_THREADS = 192;   // wgrad: producer warp, MMA warp, 4 bias/flush warps
 
 // ------------------------------------------------------------------------------------------ W^T packing
 // block (l, nh, ks): rows = input feature i (256 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
@@ -60,28 +45,28 @@ struct DgradParams {
   int64_t M;
   int num_tiles;
   const uint8_t *packed;    // forward pack + W^T blocks
-  const uint8_t *save_c;    // [tiles][8][128 KB]
-  uint8_t *save_d;          // [tiles][8][128 KB]  dpre_l images (output)
+  const uint8_t *save_pre;  // [tiles][8][128 KB] pre-activation images
+  uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
-__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 16 W^T blocks
 
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sW = base + A_BYTES, sBar = sW + NSTAGE * WBLK_BYTES;
-  uint8_t *gA = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  uint8_t *gA = smem_raw;
+  const uint32_t sA = base, sW = base + A_BYTES, sBar = sW + NSTAGE * WBLK_BYTES + BIAS_BYTES;
   auto bar_full = [&](int s) { return sBar + 8u * s; };
   auto bar_empty = [&](int s) { return sBar + 8u * (NSTAGE + s); };
   const uint32_t bar_acc = sBar + 8u * (2 * NSTAGE), bar_aready = sBar + 8u * (2 * NSTAGE + 1);
   const uint32_t tmem_slot = sBar + 8u * (2 * NSTAGE + 2);
-  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(gA + A_BYTES + NSTAGE * WBLK_BYTES + 8 * (2 * NSTAGE + 2));
+  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_aready, 128);
+    mbar_init(bar_aready, N_EPI);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -90,12 +75,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const Dgrad
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot_g;
   const uint8_t *wt = p.packed + PACK_WT_OFF;
-  const float *w_out = reinterpret_cast<const float *>(p.packed + PACK_W_BYTES) + NH * D;
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_empty(s), ph ^ 1);
+        mbar_arrive_expect_tx(bar_full(s), WOUT_BYTES);
+        bulk_g2s(sW + s * WBLK_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar_full(s));
+        if (++s == NSTAGE) { s = 0; ph ^= 1; }
         for (int l = NH - 1; l >= 1; --l)
           for (int b = 0; b < 16; ++b) {
             mbar_wait(bar_empty(s), ph ^ 1);
@@ -103,12 +91,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const Dgrad
             bulk_g2s(sW + s * WBLK_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES, WBLK_BYTES, bar_full(s));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(128, 256);
       int s = 0; uint32_t ph = 0, ph_a = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (++s == NSTAGE) { s = 0; ph ^= 1; }        // W_out pseudo-block: consumed by the epilogue warps
         for (int l = NH - 1; l >= 1; --l) {
           mbar_wait(bar_aready, ph_a); ph_a ^= 1;
           tcgen05_fence_after();
@@ -127,38 +117,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const Dgrad
             }
           mma_commit(bar_acc);
         }
+      }
     }
   } else {
-    const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 64;
-    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
+    // epilogue warps: thread = (row, column half); 8 groups of 32 columns each
+    const int e = warp - 2, q = warp & 3, half = e >> 2, row = q * 32 + lane, et = threadIdx.x - 64;
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
     uint32_t ph_acc = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int ring_pos = 0;
+    // byte offset of the 4 chunks of column group g (32 columns) of this thread's half, inside a 128 KB image
+    auto chunk_off = [&](int g, int c) {
+      const int col0 = half * 256 + g * 32;
+      return (uint32_t)((col0 >> 6) * SLAB_BYTES + sw128_chunk_off(row, ((col0 & 63) >> 3) + c));
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ring_pos += DG_RING_PER_TILE) {
       const int64_t m = (int64_t)tile * TILE_M + row;
-      const uint8_t *c_tile = p.save_c + (int64_t)tile * NH * A_BYTES;
+      const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * A_BYTES;
       uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
-      // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos_7
+      // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7)
       {
-        if (et == 0) bulk_wait_read_all();
-        named_bar_sync(1, 128);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
-        const uint8_t *c7 = c_tile + (int64_t)(NH - 1) * A_BYTES;
+        const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
+        uint4 pvA[4], pvB[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(0, c));
+        if (et == 0) bulk_wait_read_all();            // previous tile's last bulk store has left the A image
+        named_bar_sync(1, N_EPI);
+        const int slot = ring_pos;                    // W_out pseudo-block
+        mbar_wait(bar_full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+        const float *wout_s = reinterpret_cast<const float *>(gA + A_BYTES + (slot % NSTAGE) * WBLK_BYTES);
+        auto prologue_group = [&](const uint4 (&pv)[4], int g) {
+          const int col0 = half * 256 + g * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col0 + c * 8), wa1 = *reinterpret_cast<const float4 *>(wout_s + col0 + c * 8 + 4);
+            const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col0 + c * 8), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col0 + c * 8 + 4);
+            uint4 o;
+            o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * __cosf(bf_lo(pv[c].x)), (gg.x * wa0.y + gg.y * wb0.y) * __cosf(bf_hi(pv[c].x)));
+            o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * __cosf(bf_lo(pv[c].y)), (gg.x * wa0.w + gg.y * wb0.w) * __cosf(bf_hi(pv[c].y)));
+            o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * __cosf(bf_lo(pv[c].z)), (gg.x * wa1.y + gg.y * wb1.y) * __cosf(bf_hi(pv[c].z)));
+            o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * __cosf(bf_lo(pv[c].w)), (gg.x * wa1.w + gg.y * wb1.w) * __cosf(bf_hi(pv[c].w)));
+            *reinterpret_cast<uint4 *>(gA + chunk_off(g, c)) = o;
+          }
+        };
 #pragma unroll 1
-        for (int c = 0; c < D / 8; ++c) {       // 64 chunks of 8 columns
-          const uint32_t off = (c >> 3) * SLAB_BYTES + sw128_chunk_off(row, c & 7);
-          const uint4 cv = *reinterpret_cast<const uint4 *>(c7 + off);
-          const float4 wa0 = __ldg(reinterpret_cast<const float4 *>(w_out + c * 8)), wa1 = __ldg(reinterpret_cast<const float4 *>(w_out + c * 8 + 4));
-          const float4 wb0 = __ldg(reinterpret_cast<const float4 *>(w_out + D + c * 8)), wb1 = __ldg(reinterpret_cast<const float4 *>(w_out + D + c * 8 + 4));
-          uint4 o;
-          o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * bf_lo(cv.x), (gg.x * wa0.y + gg.y * wb0.y) * bf_hi(cv.x));
-          o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * bf_lo(cv.y), (gg.x * wa0.w + gg.y * wb0.w) * bf_hi(cv.y));
-          o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * bf_lo(cv.z), (gg.x * wa1.y + gg.y * wb1.y) * bf_hi(cv.z));
-          o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * bf_lo(cv.w), (gg.x * wa1.w + gg.y * wb1.w) * bf_hi(cv.w));
-          *reinterpret_cast<uint4 *>(gA + off) = o;
+        for (int g = 0; g < 8; g += 2) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(g + 1, c));
+          prologue_group(pvA, g);
+          if (g + 2 < 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(g + 2, c));
+          }
+          prologue_group(pvB, g + 1);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, N_EPI);
         if (et == 0) {
+          mbar_arrive(bar_empty(slot % NSTAGE));      // W_out slot back to the producer
           uint8_t *dst = d_tile + (int64_t)(NH - 1) * A_BYTES;
 #pragma unroll 1
           for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
@@ -168,34 +185,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const Dgrad
         mbar_arrive(bar_aready);
       }
       for (int l = NH - 1; l >= 1; --l) {
-        // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos_{l-1} -> dpre_{l-1}
+        // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos(pre_{l-1}) -> dpre_{l-1}
+        const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * A_BYTES;
+        uint4 pvA[4], pvB[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(0, c));   // in flight during the MMAs
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(1, c));
         mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
         tcgen05_fence_after();
         if (et == 0) bulk_wait_read_all();
-        named_bar_sync(1, 128);
-        const uint8_t *cprev = c_tile + (int64_t)(l - 1) * A_BYTES;
-#pragma unroll 1
-        for (int g = 0; g < D / 32; ++g) {
-          uint4 cv[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            cv[c] = *reinterpret_cast<const uint4 *>(cprev + (g >> 1) * SLAB_BYTES + sw128_chunk_off(row, (g & 1) * 4 + c));
-          uint32_t acc[32];
-          tmem_ld32(tm_row + g * 32, acc);
-          tmem_ld_wait();
+        named_bar_sync(1, N_EPI);
+        uint32_t accA[32], accB[32];
+        tmem_ld32(tm_row, accA);
+        auto process = [&](const uint32_t (&acc)[32], const uint4 (&pv)[4], int g) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t off = (g >> 1) * SLAB_BYTES + sw128_chunk_off(row, (g & 1) * 4 + c);
             uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * bf_lo(cv[c].x), __uint_as_float(acc[c * 8 + 1]) * bf_hi(cv[c].x));
-            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * bf_lo(cv[c].y), __uint_as_float(acc[c * 8 + 3]) * bf_hi(cv[c].y));
-            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * bf_lo(cv[c].z), __uint_as_float(acc[c * 8 + 5]) * bf_hi(cv[c].z));
-            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * bf_lo(cv[c].w), __uint_as_float(acc[c * 8 + 7]) * bf_hi(cv[c].w));
-            *reinterpret_cast<uint4 *>(gA + off) = o;
+            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * __cosf(bf_lo(pv[c].x)), __uint_as_float(acc[c * 8 + 1]) * __cosf(bf_hi(pv[c].x)));
+            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * __cosf(bf_lo(pv[c].y)), __uint_as_float(acc[c * 8 + 3]) * __cosf(bf_hi(pv[c].y)));
+            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * __cosf(bf_lo(pv[c].z)), __uint_as_float(acc[c * 8 + 5]) * __cosf(bf_hi(pv[c].z)));
+            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * __cosf(bf_lo(pv[c].w)), __uint_as_float(acc[c * 8 + 7]) * __cosf(bf_hi(pv[c].w)));
+            *reinterpret_cast<uint4 *>(gA + chunk_off(g, c)) = o;
+          }
+        };
+#pragma unroll 1
+        for (int g = 0; g < 8; g += 2) {
+          tmem_ld_wait(accA);
+          tmem_ld32(tm_row + (g + 1) * 32, accB);
+          process(accA, pvA, g);
+          if (g + 2 < 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(g + 2, c));
+          }
+          tmem_ld_wait(accB);
+          if (g + 2 < 8) tmem_ld32(tm_row + (g + 2) * 32, accA);
+          process(accB, pvB, g + 1);
+          if (g + 3 < 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(g + 3, c));
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, N_EPI);
         if (et == 0) {
           uint8_t *dst = d_tile + (int64_t)(l - 1) * A_BYTES;
 #pragma unroll 1
@@ -220,7 +252,7 @@ constexpr int WG_KSTAGE = 32;                           // points per pipeline s
 constexpr int WG_SLAB_STAGE = WG_KSTAGE * 128;          // 4 KB: 32 rows of one 64-feature slab
 constexpr int WG_STAGE_BYTES = 10 * WG_SLAB_STAGE;      // 2 (o-block) + 8 (all i) slabs = 40 KB
 constexpr int WG_NSTAGE = 5;
-constexpr int WG_SMEM_BYTES = WG_NSTAGE * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_SMEM_BYTES = WG_NSTAGE * WG_STAGE_BYTES + 256;
 
 struct WgradParams {
   const uint8_t *save_d, *save_h, *save_enc;
@@ -233,10 +265,11 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_wgrad_bf16_kernel(const WgradParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *gS = smem_raw + (base - smem_u32(smem_raw));
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  uint8_t *gS = smem_raw;
   const uint32_t sBar = base + WG_NSTAGE * WG_STAGE_BYTES;
   auto bar_full = [&](int s) { return sBar + 8u * s; };
   auto bar_empty = [&](int s) { return sBar + 8u * (WG_NSTAGE + s); };
@@ -413,8 +446,6 @@ __global__ void __launch_bounds__(128) out_wgrad_bf16_kernel(const float2 *__res
 
 using namespace snf;
 
-int64_t snf_bf16_pack_total_bytes() { return bf::PACK_TOTAL_BYTES; }
-
 int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
   const int64_t chunks = (int64_t)bf::WT_BLOCKS * (bf::WBLK_BYTES / 16);
   bf::pack_wt_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(
@@ -423,9 +454,8 @@ int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
   return launch_status();
 }
 
-// ws layout (shared with snf_mlp_bf16.cu): [enc][H][C][D]
-int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, uint8_t *enc, uint8_t *h, uint8_t *c, uint8_t *d,
-                      float *const *gW, float *const *gB, int num_sms, cudaStream_t st) {
+int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
+                      float *const *gB, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
@@ -445,12 +475,12 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, uint
   dp.g = reinterpret_cast<const float2 *>(grad_out);
   dp.M = M; dp.num_tiles = num_tiles;
   dp.packed = reinterpret_cast<const uint8_t *>(packed);
-  dp.save_c = c; dp.save_d = d;
+  dp.save_pre = w.pre; dp.save_d = w.d;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(dp);
 
   bf::WgradParams wp{};
-  wp.save_d = d; wp.save_h = h; wp.save_enc = enc;
+  wp.save_d = w.d; wp.save_h = w.h; wp.save_enc = w.enc;
   wp.num_tiles = num_tiles;
   int tpi = (num_tiles * 32 + 1023) / 1024;
   if (tpi < 4) tpi = 4;
@@ -458,10 +488,10 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, uint
   wp.num_items = ((num_tiles + tpi - 1) / tpi) * 32;
   for (int l = 0; l < bf::NH; ++l) { wp.gW[l] = gW[l]; wp.gB[l] = gB[l]; }
   const int wgrid = wp.num_items < num_sms ? wp.num_items : num_sms;
-  bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::NTHREADS, bf::WG_SMEM_BYTES, st>>>(wp);
+  bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::WG_THREADS, bf::WG_SMEM_BYTES, st>>>(wp);
 
   const int tpc = (num_tiles + 4 * num_sms - 1) / (4 * num_sms);
-  bf::out_wgrad_bf16_kernel<<<(num_tiles + tpc - 1) / tpc, 128, 0, st>>>(dp.g, M, num_tiles, tpc, h, gW[bf::NH], gB[bf::NH]);
+  bf::out_wgrad_bf16_kernel<<<(num_tiles + tpc - 1) / tpc, 128, 0, st>>>(dp.g, M, num_tiles, tpc, w.h, gW[bf::NH], gB[bf::NH]);
   count_launch(3);
   return launch_status();
 }
