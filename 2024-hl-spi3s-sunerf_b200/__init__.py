@@ -20,7 +20,7 @@ from .model import NeRF, NeRF_DT, EmissionModel, PositionalEncoding, Sine, Simpl
 from .sampling import StratifiedSampler, HierarchicalSampler
 from .rendering import SuNeRFRendering, EmissionRadiativeTransfer, DensityTemperatureRadiativeTransfer
 from .trainer import RayTrainer, ImageAsinhScaling
-from . import rays
+from . import rays, parallel
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
            'StratifiedSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',

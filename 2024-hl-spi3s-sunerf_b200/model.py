@@ -58,9 +58,8 @@ class _FieldMLP(torch.autograd.Function):
     """x[M,4] -> raw[M,2]; saves the layer activations in a workspace for the analytic backward."""
 
     @staticmethod
-    def forward(ctx, x, owner, off0, off1, *params):
+    def forward(ctx, x, owner, train, off0, off1, *params):
         weights, biases = list(params[0::2]), list(params[1::2])
-        train = any(ctx.needs_input_grad[4:])
         mode = owner.precision
         packed = owner._packed_ptr(weights, biases) if mode == 'bf16' else None
         out, ws = ops.mlp_forward(x, weights, biases, (off0, off1), mode=mode, train=train, packed_ptr=packed)
@@ -79,7 +78,7 @@ class _FieldMLP(torch.autograd.Function):
         flat = []
         for gw, gb in zip(gws, gbs):
             flat += [gw, gb]
-        return (None, None, None, None, *flat)
+        return (None, None, None, None, None, *flat)
 
 
 class NeRF(nn.Module):
@@ -124,7 +123,10 @@ class NeRF(nn.Module):
 
     def raw(self, x: torch.Tensor) -> torch.Tensor:
         off0, off1 = self._out_offsets()
-        return _FieldMLP.apply(x.reshape(-1, 4), self, off0, off1, *self.linear_params())
+        params = self.linear_params()
+        # activations are only kept (and the workspace only sized for them) when a backward can follow
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _FieldMLP.apply(x.reshape(-1, 4), self, train, off0, off1, *params)
 
     def forward(self, x: torch.Tensor):
         return {'inferences': self.raw(x)}

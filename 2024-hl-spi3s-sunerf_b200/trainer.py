@@ -14,7 +14,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import ops
+from . import ops, parallel
 from ._lib import SnfError
 from .rendering import DensityTemperatureRadiativeTransfer, SuNeRFRendering
 
@@ -158,9 +158,7 @@ class RayTrainer:
             g_raw_c = ops.composite_emission_bwd(raw_c, z, rays_d, g_ic.view(-1), None)
         ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
         h_coarse = self._reduce_async('coarse_model')
-        for h in (h_fine, h_coarse):
-            if h is not None:
-                h.wait()
+        parallel.wait_all([h_fine, h_coarse])
         # ---- optimiser (grads averaged over ranks == Lightning dp's mean of replica losses)
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.scratch,
@@ -173,10 +171,8 @@ class RayTrainer:
                 'z_vals_hierarchical': new_z}
 
     def _reduce_async(self, name):
-        if self.world == 1:
-            return None
         lo, hi = self.model_range[name]
-        return torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True)
+        return parallel.allreduce_sum_async(self.flat_grad, lo, hi, self.pg)
 
     def check_finite(self) -> None:
         """The reference asserts on NaN/Inf every step (sunerf.py:105-107); here it is one device flag read on demand."""
