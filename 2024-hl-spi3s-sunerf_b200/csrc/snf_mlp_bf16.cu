@@ -20,7 +20,8 @@ namespace snf {
 namespace bf {
 
 // ------------------------------------------------------------------------------------------ weight packing
-// one thread per 16-byte chunk of the packed image; block order = consumption order (layer, n-half, k-slab)
+// one thread per 16-byte chunk of the packed image; 16 KB blocks of 128 output features x 64 k in consumption order
+// (layer, 128-feature chunk q, k-slab); CTA r of a pair streams rows [64r, 64r+64) of every block
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, const float *w1, const float *w2,
                                                            const float *w3, const float *w4, const float *w5,
                                                            const float *w6, const float *w7, uint4 *__restrict__ dst) {
@@ -29,13 +30,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, cons
   if (idx >= (int64_t)FWD_BLOCKS * (WBLK_BYTES / 16)) return;
   const int blk = (int)(idx / (WBLK_BYTES / 16));
   const int within = (int)(idx % (WBLK_BYTES / 16));
-  int l, nh, ks;
-  if (blk < 4) { l = 0; nh = blk >> 1; ks = blk & 1; }
-  else { const int b = blk - 4; l = 1 + b / 16; nh = (b % 16) >> 3; ks = b & 7; }
-  const int r = within >> 3;                 // row inside the block (0..255)
+  int l, q, ks;
+  if (blk < 8) { l = 0; q = blk >> 1; ks = blk & 1; }
+  else { const int b2 = blk - 8; l = 1 + b2 / 32; q = (b2 % 32) >> 3; ks = b2 & 7; }
+  const int r = within >> 3;                 // row inside the block (0..127)
   const int pos = within & 7;                // stored chunk position inside the 128 B row
   const int c8 = pos ^ (r & 7);              // logical chunk (SWIZZLE_128B)
-  const int n = nh * WBLK_ROWS + r;
+  const int n = q * NCHUNK + r;
   const int kbase = ks * 64 + c8 * 8;
   const int kin = l == 0 ? 84 : D;
   float v[8];
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float *b0, const 
 struct FwdParams {
   const float4 *x;        // [M] (x,y,z,t)
   int64_t M;
-  int num_tiles;
+  int num_tiles;          // rounded up to even: a CTA pair always runs two tiles
   const uint8_t *packed;  // PACK_TOTAL_BYTES
   float2 *out;            // [M]
   float off0, off1;
@@ -84,81 +85,92 @@ struct FwdParams {
 
 constexpr int FWD_RING_PER_TILE = FWD_BLOCKS + 1;   // + the W_out pseudo-block
 
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();   // the UMMA/TMA images need a 1024-byte aligned window
   uint8_t *gA = smem_raw;
-  const uint32_t sA = base, sW = base + A_BYTES, sBias = sW + NSTAGE * WBLK_BYTES, sBar = sBias + BIAS_BYTES;
-  float *bias_s = reinterpret_cast<float *>(smem_raw + A_BYTES + NSTAGE * WBLK_BYTES);
-  auto bar_full = [&](int s) { return sBar + 8u * s; };
-  auto bar_empty = [&](int s) { return sBar + 8u * (NSTAGE + s); };
-  const uint32_t bar_acc = sBar + 8u * (2 * NSTAGE), bar_aready = sBar + 8u * (2 * NSTAGE + 1);
-  const uint32_t tmem_slot = sBar + 8u * (2 * NSTAGE + 2);
-  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - base));
+  const uint32_t sA = base, sW = base + OFF_RING;
+  float *bias_s = reinterpret_cast<float *>(smem_raw + OFF_BIAS);
+  const Bars bar{base + OFF_BAR};
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_aready, N_EPI);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), 1); mbar_init(bar.empty(s), 1); mbar_init(bar.peer_full(s), 1); }
+    mbar_init(bar.acc(), 1);
+    mbar_init(bar.aready(), 2);        // leader: its own epilogue warps + the peer's
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot_g;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + OFF_BAR + 8 * (3 * NSTAGE + 2));
 
   const float *bias_all = reinterpret_cast<const float *>(p.packed + PACK_BIAS_OFF);
   const float *b_out = reinterpret_cast<const float *>(p.packed + PACK_BOUT_OFF);
 
   if (warp == 0) {
-    // =========================== TMA producer
+    // =========================== TMA producer (each CTA streams its half of every weight block)
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
         for (int blk = 0; blk < FWD_RING_PER_TILE; ++blk) {
-          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_wait_cluster(bar.empty(s), ph ^ 1);
           if (blk < FWD_BLOCKS) {
-            mbar_arrive_expect_tx(bar_full(s), WBLK_BYTES);
-            bulk_g2s(sW + s * WBLK_BYTES, p.packed + (int64_t)blk * WBLK_BYTES, WBLK_BYTES, bar_full(s));
+            mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
+            bulk_g2s(sW + s * WHALF_BYTES, p.packed + (int64_t)blk * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
           } else {
-            mbar_arrive_expect_tx(bar_full(s), WOUT_BYTES);
-            bulk_g2s(sW + s * WBLK_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar_full(s));
+            mbar_arrive_expect_tx(bar.full(s), WOUT_BYTES);
+            bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
           }
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(128, 256);
       int s = 0; uint32_t ph = 0, ph_a = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < NH; ++l) {
-          mbar_wait(bar_aready, ph_a); ph_a ^= 1;     // this layer's A image is complete, TMEM is drained
-          tcgen05_fence_after();
-          const int nslab = l == 0 ? 2 : 8;
-          for (int nh = 0; nh < 2; ++nh) {
-            for (int ks = 0; ks < nslab; ++ks) {
-              mbar_wait(bar_full(s), ph);
-              tcgen05_fence_after();
-              const int ksteps = (l == 0 && ks == 1) ? (K0 - 64) / 16 : 4;
+      if (rank == 0) {
+        // =========================== MMA issuer (leader CTA): M=256 across the pair, N=128 per instruction
+        const uint32_t idesc = idesc_bf16(256, NCHUNK);
+        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+          for (int l = 0; l < NH; ++l) {
+            mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;   // both A images complete, both TMEMs drained
+            tcgen05_fence_after();
+            const int nslab = l == 0 ? 2 : 8;
+            for (int q = 0; q < 4; ++q) {
+              for (int ks = 0; ks < nslab; ++ks) {
+                mbar_wait(bar.full(s), ph);
+                mbar_wait_cluster(bar.peer_full(s), ph);
+                tcgen05_fence_after();
+                const int ksteps = (l == 0 && ks == 1) ? (K0 - 64) / 16 : 4;
 #pragma unroll 4
-              for (int k4 = 0; k4 < ksteps; ++k4) {
-                const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
-                const uint64_t bd = smem_desc(sW + s * WBLK_BYTES + k4 * 32, 16, 1024);
-                mma_ss(tmem + nh * 256, ad, bd, idesc, (ks | k4) != 0);
+                for (int k4 = 0; k4 < ksteps; ++k4) {
+                  const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
+                  const uint64_t bd = smem_desc(sW + s * WHALF_BYTES + k4 * 32, 16, 1024);
+                  mma_ss_2cta(tmem + q * NCHUNK, ad, bd, idesc, (ks | k4) != 0);
+                }
+                mma_commit_2cta(bar.empty(s), 3);           // frees the stage in both CTAs
+                if (++s == NSTAGE) { s = 0; ph ^= 1; }
               }
-              mma_commit(bar_empty(s));               // frees the weight stage when these MMAs have read it
-              if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
+            mma_commit_2cta(bar.acc(), 3);                  // whole layer accumulated, in both CTAs
           }
-          mma_commit(bar_acc);                        // whole layer accumulated
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }            // the W_out pseudo-block is consumed by the epilogue warps
         }
-        if (++s == NSTAGE) { s = 0; ph ^= 1; }        // the W_out pseudo-block is consumed by the epilogue warps
+      } else {
+        // =========================== peer relay: tell the leader when this CTA's half of a stage has landed
+        // every ring slot is relayed (the W_out pseudo-block too) so peer_full[s] keeps the same phase as full[s]
+        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+          for (int blk = 0; blk < FWD_RING_PER_TILE; ++blk) {
+            mbar_wait(bar.full(s), ph);
+            mbar_arrive_remote(mapa_shared(bar.peer_full(s), 0));
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+        }
       }
     }
   } else {
@@ -170,13 +182,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
     const int et = threadIdx.x - 64;                  // 0..255
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
     const bool train = p.save_h != nullptr;
+    uint8_t *stg = smem_raw + OFF_STG + e * STG_WARP_BYTES;       // this warp's 4 KB staging block
+    const uint32_t stg_s = base + OFF_STG + e * STG_WARP_BYTES;
     uint32_t ph_acc = 0;
     int ring_pos = 0;                                 // ring slots consumed by earlier tiles
+    auto signal_aready = [&]() {                      // all 256 threads: fences done -> one arrival per CTA
+      tcgen05_fence_before();
+      named_bar_sync(1, N_EPI);
+      if (et == 0) {
+        if (rank == 0) mbar_arrive(bar.aready());
+        else mbar_arrive_remote(mapa_shared(bar.aready(), 0));
+      }
+    };
     // chunks 4..7 of slab 1 are never read by the layer-0 MMAs but are part of the saved encoder image
     if (half == 1)
       for (int c8 = 4; c8 < 8; ++c8)
         *reinterpret_cast<uint4 *>(gA + SLAB_BYTES + sw128_chunk_off(row, c8)) = make_uint4(0, 0, 0, 0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ring_pos += FWD_RING_PER_TILE) {
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs, ring_pos += FWD_RING_PER_TILE) {
+      const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
       // ---- layer-0 operand: positional encoding of this row, written straight into the A image.
       //      half 0: x and frequencies 0..4 ; half 1: bf16 residual of x, zero padding and frequencies 5..9
@@ -217,13 +240,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
             bulk_commit();
           }
         }
-        tcgen05_fence_before();
-        mbar_arrive(bar_aready);
+        signal_aready();
       }
       // ---- layers
       for (int l = 0; l < NH; ++l) {
         const float2 bnext = __ldg(reinterpret_cast<const float2 *>(bias_all + l * D) + et);   // in flight during the MMAs
-        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+        mbar_wait_cluster(bar.acc(), ph_acc); ph_acc ^= 1;
         tcgen05_fence_after();
         const bool last = (l == NH - 1);
         const bool write_a = !last || train;
@@ -233,8 +255,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
         const float *wout_s = nullptr;
         if (last) {   // W_out pseudo-block: ring slot ring_pos + FWD_BLOCKS
           const int slot = ring_pos + FWD_BLOCKS;
-          mbar_wait(bar_full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
-          wout_s = reinterpret_cast<const float *>(gA + A_BYTES + (slot % NSTAGE) * WBLK_BYTES);
+          mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+          wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
         }
         uint8_t *psave = train ? p.save_pre + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
         float o0 = 0.f, o1 = 0.f;
@@ -262,18 +284,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
             }
           }
           const int slab = col0 >> 6;
+          if (train && (g & 1) == 0) {   // new slab: the previous staged block must have left shared memory
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int c8 = ((col0 & 63) >> 3) + c;
-            const uint32_t off = slab * SLAB_BYTES + sw128_chunk_off(row, c8);
             if (write_a) {
               uint4 o;
               o.x = pack_bf16x2(hv[c * 8 + 0], hv[c * 8 + 1]); o.y = pack_bf16x2(hv[c * 8 + 2], hv[c * 8 + 3]);
               o.z = pack_bf16x2(hv[c * 8 + 4], hv[c * 8 + 5]); o.w = pack_bf16x2(hv[c * 8 + 6], hv[c * 8 + 7]);
-              *reinterpret_cast<uint4 *>(gA + off) = o;
+              *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c8)) = o;
             }
-            if (train)
-              *reinterpret_cast<uint4 *>(psave + off) = make_uint4(ppk[c * 4], ppk[c * 4 + 1], ppk[c * 4 + 2], ppk[c * 4 + 3]);
+            if (train)   // pre-activation: staged per warp (32 rows x 128 B, image layout), then one 4 KB bulk store
+              *reinterpret_cast<uint4 *>(stg + sw128_chunk_off(lane, c8)) = make_uint4(ppk[c * 4], ppk[c * 4 + 1], ppk[c * 4 + 2], ppk[c * 4 + 3]);
+          }
+          if (train && (g & 1) == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(psave + slab * SLAB_BYTES + (q * 32) * 128, stg_s, STG_WARP_BYTES);
+              bulk_commit();
+            }
           }
         };
 #pragma unroll 1
@@ -298,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
         if (last) {
           // combine the two column halves of each row through the (now idle) bias buffer, release the W_out slot
           named_bar_sync(1, N_EPI);
-          if (et == 0) mbar_arrive(bar_empty((ring_pos + FWD_BLOCKS) % NSTAGE));
+          if (et == 0) mbar_arrive(bar.empty((ring_pos + FWD_BLOCKS) % NSTAGE));
           if (half == 1) reinterpret_cast<float2 *>(bias_s)[row] = make_float2(o0, o1);
           named_bar_sync(1, N_EPI);
           if (half == 0 && m < p.M) {
@@ -306,16 +339,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdPara
             p.out[m] = make_float2((o0 + o.x) + __ldg(b_out) + p.off0, (o1 + o.y) + __ldg(b_out + 1) + p.off1);
           }
         } else {
-          tcgen05_fence_before();
-          mbar_arrive(bar_aready);
+          signal_aready();
         }
       }
     }
-    if (train && et == 0) bulk_wait_all();
+    if (train && lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  cluster_sync_all();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc_2cta(tmem, 512); }
 }
 
 }  // namespace bf
@@ -374,6 +406,7 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   p.x = reinterpret_cast<const float4 *>(x);
   p.M = M;
   p.num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
+  p.num_tiles = (p.num_tiles + 1) / 2 * 2;
   p.packed = reinterpret_cast<const uint8_t *>(packed);
   p.out = reinterpret_cast<float2 *>(out);
   p.off0 = off0; p.off1 = off1;
@@ -381,7 +414,8 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
     bf::Bf16Ws w = bf::bf16_layout(ws, M, 1);
     p.save_enc = w.enc; p.save_h = w.h; p.save_pre = w.pre;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  grid &= ~1;   // whole CTA pairs
   bf::mlp_fwd_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   count_launch();
   return launch_status();

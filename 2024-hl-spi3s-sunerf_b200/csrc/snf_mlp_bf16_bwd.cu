@@ -12,6 +12,8 @@
 //     over points for the bias gradients.
 //
 // This is what torch.autograd derives for NeRF.forward (sunerf/model/model.py:44-57) - restated analytically.
+#include <cstdio>
+#include <cstdlib>
 #include "snf_bf16_common.cuh"
 
 namespace snf {
@@ -20,7 +22,7 @@ namespace bf {
 constexpr int WG_THREADS = 192;   // wgrad: producer warp, MMA warp, 4 bias/flush warps
 
 // ------------------------------------------------------------------------------------------ W^T packing
-// block (l, nh, ks): rows = input feature i (256 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
+// block (l, q, ks): rows = input feature i (128 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
 __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const float *w2, const float *w3, const float *w4,
                                                       const float *w5, const float *w6, const float *w7,
                                                       uint4 *__restrict__ dst) {
@@ -28,9 +30,9 @@ __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const flo
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)WT_BLOCKS * (WBLK_BYTES / 16)) return;
   const int blk = (int)(idx / (WBLK_BYTES / 16)), within = (int)(idx % (WBLK_BYTES / 16));
-  const int li = blk / 16, nh = (blk % 16) >> 3, ks = blk & 7;
+  const int li = blk / 32, q = (blk % 32) >> 3, ks = blk & 7;
   const int r = within >> 3, pos = within & 7, c8 = pos ^ (r & 7);
-  const int i = nh * 256 + r, o0 = ks * 64 + c8 * 8;
+  const int i = q * NCHUNK + r, o0 = ks * 64 + c8 * 8;
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = W[li][(o0 + j) * D + i];
@@ -43,188 +45,203 @@ __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const flo
 struct DgradParams {
   const float2 *g;          // [M] dL/d out
   int64_t M;
-  int num_tiles;
+  int num_tiles;            // even
   const uint8_t *packed;    // forward pack + W^T blocks
   const uint8_t *save_pre;  // [tiles][8][128 KB] pre-activation images
   uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
-constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 16 W^T blocks
+constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 32 W^T blocks
 
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
   uint8_t *gA = smem_raw;
-  const uint32_t sA = base, sW = base + A_BYTES, sBar = sW + NSTAGE * WBLK_BYTES + BIAS_BYTES;
-  auto bar_full = [&](int s) { return sBar + 8u * s; };
-  auto bar_empty = [&](int s) { return sBar + 8u * (NSTAGE + s); };
-  const uint32_t bar_acc = sBar + 8u * (2 * NSTAGE), bar_aready = sBar + 8u * (2 * NSTAGE + 1);
-  const uint32_t tmem_slot = sBar + 8u * (2 * NSTAGE + 2);
-  volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - base));
+  const uint32_t sA = base, sW = base + OFF_RING;
+  const Bars bar{base + OFF_BAR};
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_aready, N_EPI);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), 1); mbar_init(bar.empty(s), 1); mbar_init(bar.peer_full(s), 1); }
+    mbar_init(bar.acc(), 1);
+    mbar_init(bar.aready(), 2);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot_g;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + OFF_BAR + 8 * (3 * NSTAGE + 2));
   const uint8_t *wt = p.packed + PACK_WT_OFF;
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_arrive_expect_tx(bar_full(s), WOUT_BYTES);
-        bulk_g2s(sW + s * WBLK_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar_full(s));
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+        mbar_wait_cluster(bar.empty(s), ph ^ 1);
+        mbar_arrive_expect_tx(bar.full(s), WOUT_BYTES);
+        bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
         if (++s == NSTAGE) { s = 0; ph ^= 1; }
         for (int l = NH - 1; l >= 1; --l)
-          for (int b = 0; b < 16; ++b) {
-            mbar_wait(bar_empty(s), ph ^ 1);
-            mbar_arrive_expect_tx(bar_full(s), WBLK_BYTES);
-            bulk_g2s(sW + s * WBLK_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES, WBLK_BYTES, bar_full(s));
+          for (int b = 0; b < 32; ++b) {
+            mbar_wait_cluster(bar.empty(s), ph ^ 1);
+            mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
+            bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 32 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(128, 256);
       int s = 0; uint32_t ph = 0, ph_a = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        if (++s == NSTAGE) { s = 0; ph ^= 1; }        // W_out pseudo-block: consumed by the epilogue warps
-        for (int l = NH - 1; l >= 1; --l) {
-          mbar_wait(bar_aready, ph_a); ph_a ^= 1;
-          tcgen05_fence_after();
-          for (int nh = 0; nh < 2; ++nh)
-            for (int ks = 0; ks < 8; ++ks) {
-              mbar_wait(bar_full(s), ph);
-              tcgen05_fence_after();
+      if (rank == 0) {
+        const uint32_t idesc = idesc_bf16(256, NCHUNK);
+        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }        // W_out pseudo-block: consumed by the epilogue warps
+          for (int l = NH - 1; l >= 1; --l) {
+            mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;
+            tcgen05_fence_after();
+            for (int q = 0; q < 4; ++q)
+              for (int ks = 0; ks < 8; ++ks) {
+                mbar_wait(bar.full(s), ph);
+                mbar_wait_cluster(bar.peer_full(s), ph);
+                tcgen05_fence_after();
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
-                const uint64_t bd = smem_desc(sW + s * WBLK_BYTES + k4 * 32, 16, 1024);
-                mma_ss(tmem + nh * 256, ad, bd, idesc, (ks | k4) != 0);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
+                  const uint64_t bd = smem_desc(sW + s * WHALF_BYTES + k4 * 32, 16, 1024);
+                  mma_ss_2cta(tmem + q * NCHUNK, ad, bd, idesc, (ks | k4) != 0);
+                }
+                mma_commit_2cta(bar.empty(s), 3);
+                if (++s == NSTAGE) { s = 0; ph ^= 1; }
               }
-              mma_commit(bar_empty(s));
-              if (++s == NSTAGE) { s = 0; ph ^= 1; }
-            }
-          mma_commit(bar_acc);
+            mma_commit_2cta(bar.acc(), 3);
+          }
+        }
+      } else {
+        // every ring slot is relayed (the W_out pseudo-block too) so peer_full[s] keeps the same phase as full[s]
+        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+          for (int blk = 0; blk < DG_RING_PER_TILE; ++blk) {
+            mbar_wait(bar.full(s), ph);
+            mbar_arrive_remote(mapa_shared(bar.peer_full(s), 0));
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
   } else {
-    // epilogue warps: thread = (row, column half); 8 groups of 32 columns each
+    // epilogue warps: thread = (row, column half); 4 slabs (2 groups of 32 columns each) per thread and layer
     const int e = warp - 2, q = warp & 3, half = e >> 2, row = q * 32 + lane, et = threadIdx.x - 64;
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
+    uint8_t *stg = smem_raw + OFF_STG + e * STG_WARP_BYTES;
+    const uint32_t stg_s = base + OFF_STG + e * STG_WARP_BYTES;
     uint32_t ph_acc = 0;
     int ring_pos = 0;
-    // byte offset of the 4 chunks of column group g (32 columns) of this thread's half, inside a 128 KB image
-    auto chunk_off = [&](int g, int c) {
-      const int col0 = half * 256 + g * 32;
-      return (uint32_t)((col0 >> 6) * SLAB_BYTES + sw128_chunk_off(row, ((col0 & 63) >> 3) + c));
+    auto signal_aready = [&]() {
+      tcgen05_fence_before();
+      named_bar_sync(1, N_EPI);
+      if (et == 0) {
+        if (rank == 0) mbar_arrive(bar.aready());
+        else mbar_arrive_remote(mapa_shared(bar.aready(), 0));
+      }
     };
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ring_pos += DG_RING_PER_TILE) {
+    // coalesced fetch of this warp's 32 rows of one pre-activation slab (4 KB, contiguous in the image) into staging
+    auto fetch_slab = [&](const uint8_t *img, int slab) {
+      const uint8_t *src = img + slab * SLAB_BYTES + (q * 32) * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cp_async16(stg_s + i * 512 + lane * 16, src + i * 512 + lane * 16);
+      cp_async_commit();
+    };
+    // this thread's row of the staged slab: 8 chunks of 8 bf16 (logical order)
+    auto read_row = [&](uint4 (&pv)[8]) {
+      cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) pv[c] = *reinterpret_cast<const uint4 *>(stg + sw128_chunk_off(lane, c));
+      __syncwarp();                                   // everyone has read: staging may be refilled
+    };
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs, ring_pos += DG_RING_PER_TILE) {
+      const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
       const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * A_BYTES;
       uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
       // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7)
       {
+        const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
+        fetch_slab(p7, half * 4);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
-        const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
-        uint4 pvA[4], pvB[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(0, c));
         if (et == 0) bulk_wait_read_all();            // previous tile's last bulk store has left the A image
         named_bar_sync(1, N_EPI);
         const int slot = ring_pos;                    // W_out pseudo-block
-        mbar_wait(bar_full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
-        const float *wout_s = reinterpret_cast<const float *>(gA + A_BYTES + (slot % NSTAGE) * WBLK_BYTES);
-        auto prologue_group = [&](const uint4 (&pv)[4], int g) {
-          const int col0 = half * 256 + g * 32;
+        mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+        const float *wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int slab = half * 4 + j;
+          uint4 pv[8];
+          read_row(pv);
+          if (j + 1 < 4) fetch_slab(p7, slab + 1);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col0 + c * 8), wa1 = *reinterpret_cast<const float4 *>(wout_s + col0 + c * 8 + 4);
-            const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col0 + c * 8), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col0 + c * 8 + 4);
+          for (int c = 0; c < 8; ++c) {
+            const int col = slab * 64 + c * 8;
+            const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col), wa1 = *reinterpret_cast<const float4 *>(wout_s + col + 4);
+            const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col + 4);
             uint4 o;
             o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * __cosf(bf_lo(pv[c].x)), (gg.x * wa0.y + gg.y * wb0.y) * __cosf(bf_hi(pv[c].x)));
             o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * __cosf(bf_lo(pv[c].y)), (gg.x * wa0.w + gg.y * wb0.w) * __cosf(bf_hi(pv[c].y)));
             o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * __cosf(bf_lo(pv[c].z)), (gg.x * wa1.y + gg.y * wb1.y) * __cosf(bf_hi(pv[c].z)));
             o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * __cosf(bf_lo(pv[c].w)), (gg.x * wa1.w + gg.y * wb1.w) * __cosf(bf_hi(pv[c].w)));
-            *reinterpret_cast<uint4 *>(gA + chunk_off(g, c)) = o;
+            *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c)) = o;
           }
-        };
-#pragma unroll 1
-        for (int g = 0; g < 8; g += 2) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(g + 1, c));
-          prologue_group(pvA, g);
-          if (g + 2 < 8) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(p7 + chunk_off(g + 2, c));
-          }
-          prologue_group(pvB, g + 1);
         }
         fence_proxy_async_smem();
         named_bar_sync(1, N_EPI);
         if (et == 0) {
-          mbar_arrive(bar_empty(slot % NSTAGE));      // W_out slot back to the producer
+          mbar_arrive(bar.empty(slot % NSTAGE));      // W_out slot back to the producer
           uint8_t *dst = d_tile + (int64_t)(NH - 1) * A_BYTES;
 #pragma unroll 1
           for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
           bulk_commit();
         }
-        tcgen05_fence_before();
-        mbar_arrive(bar_aready);
+        signal_aready();
       }
       for (int l = NH - 1; l >= 1; --l) {
         // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos(pre_{l-1}) -> dpre_{l-1}
         const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * A_BYTES;
-        uint4 pvA[4], pvB[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(0, c));   // in flight during the MMAs
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(1, c));
-        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+        fetch_slab(pprev, half * 4);                  // in flight during the MMAs
+        mbar_wait_cluster(bar.acc(), ph_acc); ph_acc ^= 1;
         tcgen05_fence_after();
         if (et == 0) bulk_wait_read_all();
         named_bar_sync(1, N_EPI);
         uint32_t accA[32], accB[32];
         tmem_ld32(tm_row, accA);
-        auto process = [&](const uint32_t (&acc)[32], const uint4 (&pv)[4], int g) {
+        auto process = [&](const uint32_t (&acc)[32], const uint4 *pv, int slab, int c0) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+            const uint4 pw = pv[c];
             uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * __cosf(bf_lo(pv[c].x)), __uint_as_float(acc[c * 8 + 1]) * __cosf(bf_hi(pv[c].x)));
-            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * __cosf(bf_lo(pv[c].y)), __uint_as_float(acc[c * 8 + 3]) * __cosf(bf_hi(pv[c].y)));
-            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * __cosf(bf_lo(pv[c].z)), __uint_as_float(acc[c * 8 + 5]) * __cosf(bf_hi(pv[c].z)));
-            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * __cosf(bf_lo(pv[c].w)), __uint_as_float(acc[c * 8 + 7]) * __cosf(bf_hi(pv[c].w)));
-            *reinterpret_cast<uint4 *>(gA + chunk_off(g, c)) = o;
+            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * __cosf(bf_lo(pw.x)), __uint_as_float(acc[c * 8 + 1]) * __cosf(bf_hi(pw.x)));
+            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * __cosf(bf_lo(pw.y)), __uint_as_float(acc[c * 8 + 3]) * __cosf(bf_hi(pw.y)));
+            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * __cosf(bf_lo(pw.z)), __uint_as_float(acc[c * 8 + 5]) * __cosf(bf_hi(pw.z)));
+            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * __cosf(bf_lo(pw.w)), __uint_as_float(acc[c * 8 + 7]) * __cosf(bf_hi(pw.w)));
+            *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c0 + c)) = o;
           }
         };
 #pragma unroll 1
-        for (int g = 0; g < 8; g += 2) {
+        for (int j = 0; j < 4; ++j) {
+          const int slab = half * 4 + j;
+          uint4 pv[8];
+          read_row(pv);
+          if (j + 1 < 4) fetch_slab(pprev, slab + 1);
           tmem_ld_wait(accA);
-          tmem_ld32(tm_row + (g + 1) * 32, accB);
-          process(accA, pvA, g);
-          if (g + 2 < 8) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pvA[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(g + 2, c));
-          }
+          tmem_ld32(tm_row + (2 * j + 1) * 32, accB);
+          process(accA, pv, slab, 0);
           tmem_ld_wait(accB);
-          if (g + 2 < 8) tmem_ld32(tm_row + (g + 2) * 32, accA);
-          process(accB, pvB, g + 1);
-          if (g + 3 < 8) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pvB[c] = *reinterpret_cast<const uint4 *>(pprev + chunk_off(g + 3, c));
-          }
+          if (j + 1 < 4) tmem_ld32(tm_row + (2 * j + 2) * 32, accA);
+          process(accB, pv + 4, slab, 4);
         }
         fence_proxy_async_smem();
         named_bar_sync(1, N_EPI);
@@ -234,17 +251,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const Dgrad
           for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
           bulk_commit();
         }
-        if (l > 1) {
-          tcgen05_fence_before();
-          mbar_arrive(bar_aready);
-        }
+        if (l > 1) signal_aready();
       }
     }
     if (et == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  cluster_sync_all();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc_2cta(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
@@ -454,6 +468,17 @@ int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
   return launch_status();
 }
 
+// SNF_DEBUG_SYNC=1: synchronise after every backward kernel and name the one that failed (debug aid only)
+static int debug_sync(const char *what, cudaStream_t st) {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("SNF_DEBUG_SYNC"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return 0;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { fprintf(stderr, "[sunerf_b200] %s failed: %s\n", what, cudaGetErrorString(e)); return (int)e; }
+  fprintf(stderr, "[sunerf_b200] %s ok\n", what);
+  return 0;
+}
+
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
                       float *const *gB, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
@@ -464,7 +489,8 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  const int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
+  int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
+  num_tiles = (num_tiles + 1) / 2 * 2;   // CTA pairs; the workspace is sized for the padding tile
   // gradients are accumulated with atomics: clear them first (ABI: overwritten)
   const int64_t wsz[9] = {512 * 84, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 2 * 512};
   for (int l = 0; l <= bf::NH; ++l) {
@@ -476,8 +502,10 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   dp.M = M; dp.num_tiles = num_tiles;
   dp.packed = reinterpret_cast<const uint8_t *>(packed);
   dp.save_pre = w.pre; dp.save_d = w.d;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  grid &= ~1;
   bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(dp);
+  if (int e = debug_sync("mlp_dgrad_bf16_kernel", st)) return e;
 
   bf::WgradParams wp{};
   wp.save_d = w.d; wp.save_h = w.h; wp.save_enc = w.enc;
@@ -489,6 +517,7 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   for (int l = 0; l < bf::NH; ++l) { wp.gW[l] = gW[l]; wp.gB[l] = gB[l]; }
   const int wgrid = wp.num_items < num_sms ? wp.num_items : num_sms;
   bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::WG_THREADS, bf::WG_SMEM_BYTES, st>>>(wp);
+  if (int e = debug_sync("mlp_wgrad_bf16_kernel", st)) return e;
 
   const int tpc = (num_tiles + 4 * num_sms - 1) / (4 * num_sms);
   bf::out_wgrad_bf16_kernel<<<(num_tiles + tpc - 1) / tpc, 128, 0, st>>>(dp.g, M, num_tiles, tpc, w.h, gW[bf::NH], gB[bf::NH]);

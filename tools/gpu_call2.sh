@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "bf16 or ragged or full_size" 2>&1 | tail -40 > gpurun_out/pytest_bf16.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_all.log
 timeout 600 python bench.py --precision bf16 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16.log 2>&1
-tail -40 gpurun_out/pytest_bf16.log; tail -3 gpurun_out/bench_bf16.log
+tail -15 gpurun_out/pytest_all.log; tail -3 gpurun_out/bench_bf16.log
