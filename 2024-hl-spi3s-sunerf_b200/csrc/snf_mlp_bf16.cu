@@ -20,8 +20,8 @@ namespace snf {
 namespace bf {
 
 // ------------------------------------------------------------------------------------------ weight packing
-// one thread per 16-byte chunk of the packed image; 16 KB blocks of 128 output features x 64 k in consumption order
-// (layer, 128-feature chunk q, k-slab); CTA r of a pair streams rows [64r, 64r+64) of every block
+// one thread per 16-byte chunk of the packed image; 32 KB blocks of 256 output features x 64 k in consumption order
+// (layer, n-half, k-slab); CTA r of a pair streams rows [128r, 128r+128) of every block
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, const float *w1, const float *w2,
                                                            const float *w3, const float *w4, const float *w5,
                                                            const float *w6, const float *w7, uint4 *__restrict__ dst) {
@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, cons
   const int blk = (int)(idx / (WBLK_BYTES / 16));
   const int within = (int)(idx % (WBLK_BYTES / 16));
   int l, q, ks;
-  if (blk < 8) { l = 0; q = blk >> 1; ks = blk & 1; }
-  else { const int b2 = blk - 8; l = 1 + b2 / 32; q = (b2 % 32) >> 3; ks = b2 & 7; }
-  const int r = within >> 3;                 // row inside the block (0..127)
+  if (blk < 4) { l = 0; q = blk >> 1; ks = blk & 1; }
+  else { const int b2 = blk - 4; l = 1 + b2 / 16; q = (b2 % 16) >> 3; ks = b2 & 7; }
+  const int r = within >> 3;                 // row inside the block (0..255)
   const int pos = within & 7;                // stored chunk position inside the 128 B row
   const int c8 = pos ^ (r & 7);              // logical chunk (SWIZZLE_128B)
   const int n = q * NCHUNK + r;
@@ -85,7 +85,9 @@ struct FwdParams {
 
 constexpr int FWD_RING_PER_TILE = FWD_BLOCKS + 1;   // + the W_out pseudo-block
 
+template <bool TRAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdParams p) {
+  constexpr int NSTAGE = TRAIN ? NSTAGE_TRAIN : NSTAGE_INFER;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();   // the UMMA/TMA images need a 1024-byte aligned window
@@ -98,7 +100,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), 1); mbar_init(bar.empty(s), 1); mbar_init(bar.peer_full(s), 1); }
+    // leader: full[s] = its own TMA + one remote arrival from the peer's relay
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
     mbar_init(bar.acc(), 1);
     mbar_init(bar.aready(), 2);        // leader: its own epilogue warps + the peer's
     fence_barrier_init();
@@ -107,7 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + OFF_BAR + 8 * (3 * NSTAGE + 2));
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + TMEM_SLOT_OFF);
 
   const float *bias_all = reinterpret_cast<const float *>(p.packed + PACK_BIAS_OFF);
   const float *b_out = reinterpret_cast<const float *>(p.packed + PACK_BOUT_OFF);
@@ -134,17 +137,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     if (lane == 0) {
       int s = 0; uint32_t ph = 0, ph_a = 0;
       if (rank == 0) {
-        // =========================== MMA issuer (leader CTA): M=256 across the pair, N=128 per instruction
+        // =========================== MMA issuer (leader CTA): M=256 across the pair, N=256 per instruction
         const uint32_t idesc = idesc_bf16(256, NCHUNK);
         for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
           for (int l = 0; l < NH; ++l) {
             mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;   // both A images complete, both TMEMs drained
             tcgen05_fence_after();
             const int nslab = l == 0 ? 2 : 8;
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2; ++q) {
               for (int ks = 0; ks < nslab; ++ks) {
-                mbar_wait(bar.full(s), ph);
-                mbar_wait_cluster(bar.peer_full(s), ph);
+                mbar_wait_cluster(bar.full(s), ph);         // both halves of the stage have landed
                 tcgen05_fence_after();
                 const int ksteps = (l == 0 && ks == 1) ? (K0 - 64) / 16 : 4;
 #pragma unroll 4
@@ -163,11 +165,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         }
       } else {
         // =========================== peer relay: tell the leader when this CTA's half of a stage has landed
-        // every ring slot is relayed (the W_out pseudo-block too) so peer_full[s] keeps the same phase as full[s]
+        // every ring slot is relayed (the W_out pseudo-block too) so the leader's full[s] keeps the ring's phase
         for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
           for (int blk = 0; blk < FWD_RING_PER_TILE; ++blk) {
             mbar_wait(bar.full(s), ph);
-            mbar_arrive_remote(mapa_shared(bar.peer_full(s), 0));
+            mbar_arrive_remote(mapa_shared(bar.full(s), 0));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
         }
@@ -181,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;                  // 0..255
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
-    const bool train = p.save_h != nullptr;
+    constexpr bool train = TRAIN;
     uint8_t *stg = smem_raw + OFF_STG + e * STG_WARP_BYTES;       // this warp's 4 KB staging block
     const uint32_t stg_s = base + OFF_STG + e * STG_WARP_BYTES;
     uint32_t ph_acc = 0;
@@ -255,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         const float *wout_s = nullptr;
         if (last) {   // W_out pseudo-block: ring slot ring_pos + FWD_BLOCKS
           const int slot = ring_pos + FWD_BLOCKS;
-          mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+          mbar_wait_cluster(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
           wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
         }
         uint8_t *psave = train ? p.save_pre + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
@@ -398,7 +400,9 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   if (train) { SNF_CHECK_PTR(ws); SNF_CHECK_ALIGN(ws, 1024); }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -416,7 +420,8 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   grid &= ~1;   // whole CTA pairs
-  bf::mlp_fwd_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  if (train) bf::mlp_fwd_bf16_kernel<true><<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  else bf::mlp_fwd_bf16_kernel<false><<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   count_launch();
   return launch_status();
 }

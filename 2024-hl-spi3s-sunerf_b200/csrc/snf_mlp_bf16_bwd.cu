@@ -22,7 +22,7 @@ namespace bf {
 constexpr int WG_THREADS = 192;   // wgrad: producer warp, MMA warp, 4 bias/flush warps
 
 // ------------------------------------------------------------------------------------------ W^T packing
-// block (l, q, ks): rows = input feature i (128 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
+// block (l, nh, ks): rows = input feature i (256 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
 __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const float *w2, const float *w3, const float *w4,
                                                       const float *w5, const float *w6, const float *w7,
                                                       uint4 *__restrict__ dst) {
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const flo
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)WT_BLOCKS * (WBLK_BYTES / 16)) return;
   const int blk = (int)(idx / (WBLK_BYTES / 16)), within = (int)(idx % (WBLK_BYTES / 16));
-  const int li = blk / 32, q = (blk % 32) >> 3, ks = blk & 7;
+  const int li = blk / 16, q = (blk % 16) >> 3, ks = blk & 7;
   const int r = within >> 3, pos = within & 7, c8 = pos ^ (r & 7);
   const int i = q * NCHUNK + r, o0 = ks * 64 + c8 * 8;
   float v[8];
@@ -51,7 +51,8 @@ struct DgradParams {
   uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
-constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 32 W^T blocks
+constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 16 W^T blocks
+constexpr int NSTAGE = NSTAGE_TRAIN;              // the staging area is used for the coalesced pre-activation fetches
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,7 +65,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), 1); mbar_init(bar.empty(s), 1); mbar_init(bar.peer_full(s), 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
     mbar_init(bar.acc(), 1);
     mbar_init(bar.aready(), 2);
     fence_barrier_init();
@@ -73,7 +74,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + OFF_BAR + 8 * (3 * NSTAGE + 2));
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + TMEM_SLOT_OFF);
   const uint8_t *wt = p.packed + PACK_WT_OFF;
 
   if (warp == 0) {
@@ -85,10 +86,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
         if (++s == NSTAGE) { s = 0; ph ^= 1; }
         for (int l = NH - 1; l >= 1; --l)
-          for (int b = 0; b < 32; ++b) {
+          for (int b = 0; b < 16; ++b) {
             mbar_wait_cluster(bar.empty(s), ph ^ 1);
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
-            bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 32 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
+            bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
       }
@@ -103,10 +104,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           for (int l = NH - 1; l >= 1; --l) {
             mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;
             tcgen05_fence_after();
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 2; ++q)
               for (int ks = 0; ks < 8; ++ks) {
-                mbar_wait(bar.full(s), ph);
-                mbar_wait_cluster(bar.peer_full(s), ph);
+                mbar_wait_cluster(bar.full(s), ph);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
@@ -121,11 +121,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           }
         }
       } else {
-        // every ring slot is relayed (the W_out pseudo-block too) so peer_full[s] keeps the same phase as full[s]
+        // every ring slot is relayed (the W_out pseudo-block too) so the leader's full[s] keeps the ring's phase
         for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
           for (int blk = 0; blk < DG_RING_PER_TILE; ++blk) {
             mbar_wait(bar.full(s), ph);
-            mbar_arrive_remote(mapa_shared(bar.peer_full(s), 0));
+            mbar_arrive_remote(mapa_shared(bar.full(s), 0));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
         }
@@ -176,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         if (et == 0) bulk_wait_read_all();            // previous tile's last bulk store has left the A image
         named_bar_sync(1, N_EPI);
         const int slot = ring_pos;                    // W_out pseudo-block
-        mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+        mbar_wait_cluster(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
         const float *wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
