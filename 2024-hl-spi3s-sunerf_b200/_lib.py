@@ -15,7 +15,8 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, 'csrc')
 LIB_DIR = os.path.join(_PKG, 'lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libsunerf_b200.so')
+# SNF_LIB_NAME: developer-only, lets experiment builds (SNF_NVCC_EXTRA) live next to the product library
+LIB_PATH = os.path.join(LIB_DIR, os.environ.get('SNF_LIB_NAME', 'libsunerf_b200.so'))
 SOURCES = ['snf_sampling.cu', 'snf_composite.cu', 'snf_mlp_f32.cu', 'snf_mlp_bf16.cu', 'snf_mlp_bf16_bwd.cu',
            'snf_optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
@@ -53,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.makedirs(LIB_DIR, exist_ok=True)
         srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
         tmp = LIB_PATH + '.tmp.%d' % os.getpid()
-        cmd = [_nvcc()] + NVCC_FLAGS + ['-o', tmp] + srcs
+        # SNF_NVCC_EXTRA: developer-only extra flags (e.g. -DSNF_PROF for the in-kernel cycle counters)
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('SNF_NVCC_EXTRA', '').split() + ['-o', tmp] + srcs
         if verbose:
             print(' '.join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -66,6 +66,33 @@ struct Bars {
 };
 constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE_MAX + 2);
 
+// ---- forward kernel (v2, overlapped): shared-memory layout and barrier block
+//   [A image 128 KB][weight ring 5 x 16 KB][bias: 2 layers x 2 KB][W_out 4 KB][row partial sums 1 KB][barriers]
+namespace fw {
+constexpr int NSTAGE = 5;
+constexpr int OFF_RING = A_BYTES;
+constexpr int OFF_BIAS = OFF_RING + NSTAGE * WHALF_BYTES;
+constexpr int OFF_WOUT = OFF_BIAS + 2 * BIAS_BYTES;
+constexpr int OFF_OSUM = OFF_WOUT + WOUT_BYTES;
+constexpr int OFF_BAR = OFF_OSUM + TILE_M * 8;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "forward kernel exceeds the 227 KB shared-memory window");
+//   full[s] / empty[s] : weight ring, as in Bars
+//   acc[h]             : temporal N-half h (output columns [256h, 256h+256)) of the current layer accumulated
+//                        (multicast tcgen05.commit -> both CTAs)
+//   ready[k] (leader)  : 16 arrivals = 8 epilogue warps x 2 CTAs.  k=0: A slabs 0..3 written (and D half 0 drained);
+//                        k=1..4: A slab 3+k written; k=4 also means D half 1 drained
+struct Bars {
+  uint32_t base;
+  __device__ uint32_t full(int s) const { return base + 8u * s; }
+  __device__ uint32_t empty(int s) const { return base + 8u * (NSTAGE + s); }
+  __device__ uint32_t acc(int h) const { return base + 8u * (2 * NSTAGE + h); }
+  __device__ uint32_t ready(int k) const { return base + 8u * (2 * NSTAGE + 2 + k); }
+  __device__ uint32_t tmem_slot() const { return base + 8u * (2 * NSTAGE + 7); }
+};
+constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
+}  // namespace fw
+
 // saved-image workspace (training): [enc][H = sin(pre)][P = pre][D = dL/dpre], all [tile][layer][128 KB] bf16 images.
 // Sized for an even number of tiles (CTA pairs always process two).
 struct Bf16Ws {

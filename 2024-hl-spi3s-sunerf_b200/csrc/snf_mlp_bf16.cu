@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float *b0, const 
 }
 
 // ------------------------------------------------------------------------------------------ fused forward
+constexpr int PAIR_BYTES = 32 * 128;   // 32 rows of one slab: what the two warps of a TMEM lane quarter own (4 KB, contiguous)
+
 struct FwdParams {
   const float4 *x;        // [M] (x,y,z,t)
   int64_t M;
@@ -83,139 +85,194 @@ struct FwdParams {
   uint8_t *save_pre;      // train: [tiles][8][128 KB]   pre-activation (the backward takes cos of it)
 };
 
-constexpr int FWD_RING_PER_TILE = FWD_BLOCKS + 1;   // + the W_out pseudo-block
+#ifdef SNF_PROF
+__device__ unsigned long long g_prof[2][148 * 8];
+__device__ long long g_trace[4][512];   // CTA 0, inference: clock stamps per ring block
+#define PROF_DECL(n) long long n = 0
+#define PROF_T0(t) const long long t = clock64()
+#define PROF_ADD(n, t) n += clock64() - t
+#else
+#define PROF_DECL(n)
+#define PROF_T0(t)
+#define PROF_ADD(n, t)
+#endif
+
+__device__ __forceinline__ void st_stream16(uint8_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(a, b, c, d));   // written once, read by the backward much later
+}
 
 template <bool TRAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd_bf16_kernel(const FwdParams p) {
-  constexpr int NSTAGE = TRAIN ? NSTAGE_TRAIN : NSTAGE_INFER;
+  constexpr int NSTAGE = fw::NSTAGE, OFF_RING = fw::OFF_RING, OFF_BIAS = fw::OFF_BIAS, OFF_WOUT = fw::OFF_WOUT,
+                OFF_OSUM = fw::OFF_OSUM, OFF_BAR = fw::OFF_BAR;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();   // the UMMA/TMA images need a 1024-byte aligned window
   uint8_t *gA = smem_raw;
   const uint32_t sA = base, sW = base + OFF_RING;
-  float *bias_s = reinterpret_cast<float *>(smem_raw + OFF_BIAS);
-  const Bars bar{base + OFF_BAR};
+  float *bias_s = reinterpret_cast<float *>(smem_raw + OFF_BIAS);          // [2][512]: layer l lives in buffer l & 1
+  float *wout_s = reinterpret_cast<float *>(smem_raw + OFF_WOUT);          // [2][512]
+  float2 *osum_s = reinterpret_cast<float2 *>(smem_raw + OFF_OSUM);        // [128]
+  const fw::Bars bar{base + OFF_BAR};
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *bias_all = reinterpret_cast<const float *>(p.packed + PACK_BIAS_OFF);
+  const float *b_out = reinterpret_cast<const float *>(p.packed + PACK_BOUT_OFF);
+
   if (threadIdx.x == 0) {
     // leader: full[s] = its own TMA + one remote arrival from the peer's relay
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
-    mbar_init(bar.acc(), 1);
-    mbar_init(bar.aready(), 2);        // leader: its own epilogue warps + the peer's
+    mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
+    for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
+  for (int i = threadIdx.x; i < D; i += NTHREADS) bias_s[i] = __ldg(bias_all + i);
   if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + TMEM_SLOT_OFF);
-
-  const float *bias_all = reinterpret_cast<const float *>(p.packed + PACK_BIAS_OFF);
-  const float *b_out = reinterpret_cast<const float *>(p.packed + PACK_BOUT_OFF);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::TMEM_SLOT_OFF);
 
   if (warp == 0) {
     // =========================== TMA producer (each CTA streams its half of every weight block)
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-        for (int blk = 0; blk < FWD_RING_PER_TILE; ++blk) {
-          mbar_wait_cluster(bar.empty(s), ph ^ 1);
-          if (blk < FWD_BLOCKS) {
-            mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
-            bulk_g2s(sW + s * WHALF_BYTES, p.packed + (int64_t)blk * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
-          } else {
-            mbar_arrive_expect_tx(bar.full(s), WOUT_BYTES);
-            bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
-          }
+        for (int blk = 0; blk < FWD_BLOCKS; ++blk) {
+          mbar_wait(bar.empty(s), ph ^ 1);
+#ifdef SNF_PROF
+          if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && blk < 512) g_trace[0][blk] = clock64();
+#endif
+          mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
+          bulk_g2s(sW + s * WHALF_BYTES, p.packed + (int64_t)blk * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0, ph_a = 0;
-      if (rank == 0) {
-        // =========================== MMA issuer (leader CTA): M=256 across the pair, N=256 per instruction
-        const uint32_t idesc = idesc_bf16(256, NCHUNK);
-        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-          for (int l = 0; l < NH; ++l) {
-            mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;   // both A images complete, both TMEMs drained
-            tcgen05_fence_after();
-            const int nslab = l == 0 ? 2 : 8;
-            for (int q = 0; q < 2; ++q) {
-              for (int ks = 0; ks < nslab; ++ks) {
-                mbar_wait_cluster(bar.full(s), ph);         // both halves of the stage have landed
-                tcgen05_fence_after();
-                const int ksteps = (l == 0 && ks == 1) ? (K0 - 64) / 16 : 4;
-#pragma unroll 4
-                for (int k4 = 0; k4 < ksteps; ++k4) {
-                  const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
-                  const uint64_t bd = smem_desc(sW + s * WHALF_BYTES + k4 * 32, 16, 1024);
-                  mma_ss_2cta(tmem + q * NCHUNK, ad, bd, idesc, (ks | k4) != 0);
-                }
-                mma_commit_2cta(bar.empty(s), 3);           // frees the stage in both CTAs
-                if (++s == NSTAGE) { s = 0; ph ^= 1; }
+    int s = 0; uint32_t ph = 0;
+    if (rank == 0) {
+      // =========================== MMA issuer (leader CTA): M=256 across the pair, N=256 per instruction.
+      // Layer l is accumulated as two temporal halves (D columns [0,256) then [256,512)); the first half of layer
+      // l+1 starts as soon as the epilogue has produced its k-slabs, while it is still draining half 1 of layer l.
+      // The whole warp runs the (uniform) control flow, one elected lane issues: descriptors stay in uniform registers.
+      const uint32_t idesc = idesc_bf16(256, NCHUNK);
+      const uint64_t adesc0 = smem_desc(sA, 16, 1024), bdesc0 = smem_desc(sW, 16, 1024);
+      uint32_t rph = 0;
+      PROF_DECL(t_ready); PROF_DECL(t_full); PROF_T0(t_begin);
+      auto wait_ready = [&](int k) {
+        PROF_T0(t0);
+        mbar_wait(bar.ready(k), (rph >> k) & 1u); rph ^= 1u << k;
+        PROF_ADD(t_ready, t0);
+      };
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+        int tblk = 0;
+        for (int l = 0; l < NH; ++l) {
+          const int nslab = l == 0 ? 2 : 8;
+          for (int h = 0; h < 2; ++h) {
+            if (l == 0 && h == 1) wait_ready(4);          // D half 1 drained by the previous tile's last epilogue
+            for (int ks = 0; ks < nslab; ++ks) {
+              if (h == 0) {
+                if (ks == 0) wait_ready(0);               // slabs 0..3 of the new A image (and D half 0 drained)
+                else if (ks >= 4) wait_ready(ks - 3);     // slab ks (ks == 7: D half 1 drained as well)
               }
+#ifdef SNF_PROF
+              if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[1][tblk] = clock64();
+#endif
+              {
+                PROF_T0(t0);
+                mbar_wait(bar.full(s), ph);               // both halves of the stage have landed
+                PROF_ADD(t_full, t0);
+              }
+#ifdef SNF_PROF
+              if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[2][tblk] = clock64();
+              ++tblk;
+#endif
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = adesc0 + (uint64_t)((ks * SLAB_BYTES) >> 4), bd = bdesc0 + (uint64_t)((s * WHALF_BYTES) >> 4);
+#ifndef SNF_EXP_NO_MMA
+                if (l == 0 && ks == 1) {
+#pragma unroll
+                  for (int k4 = 0; k4 < (K0 - 64) / 16; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, 1);
+                } else {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (ks | k4) != 0);
+                }
+#endif
+                mma_commit_2cta(bar.empty(s), 3);         // frees the stage in both CTAs
+                if (ks == nslab - 1) mma_commit_2cta(bar.acc(h), 3);   // this half of the layer is accumulated, in both CTAs
+              }
+              __syncwarp();
+              if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
-            mma_commit_2cta(bar.acc(), 3);                  // whole layer accumulated, in both CTAs
           }
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }            // the W_out pseudo-block is consumed by the epilogue warps
         }
-      } else {
-        // =========================== peer relay: tell the leader when this CTA's half of a stage has landed
-        // every ring slot is relayed (the W_out pseudo-block too) so the leader's full[s] keeps the ring's phase
-        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-          for (int blk = 0; blk < FWD_RING_PER_TILE; ++blk) {
-            mbar_wait(bar.full(s), ph);
-            mbar_arrive_remote(mapa_shared(bar.full(s), 0));
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
-          }
+      }
+#ifdef SNF_PROF
+      if (lane == 0) {
+        g_prof[TRAIN][blockIdx.x * 8 + 0] = clock64() - t_begin;
+        g_prof[TRAIN][blockIdx.x * 8 + 1] = t_ready;
+        g_prof[TRAIN][blockIdx.x * 8 + 2] = t_full;
+      }
+#endif
+    } else if (lane == 0) {
+      // =========================== peer relay: tell the leader when this CTA's half of a stage has landed
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+        for (int blk = 0; blk < FWD_BLOCKS; ++blk) {
+          mbar_wait(bar.full(s), ph);
+          mbar_arrive_remote_relaxed(mapa_shared(bar.full(s), 0));   // the data is TMA-written and tensor-core-read
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
   } else {
-    // =========================== epilogue warps: 256 threads, thread = (row, column half)
+    // =========================== epilogue warps: 256 threads.  Thread = (row, ch): in temporal half h, step j it owns
+    // the 32 accumulator columns 256h + 64j + 32ch .. +31, i.e. chunks 4ch..4ch+3 of A slab 4h + j.
     const int e = warp - 2;
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int half = e >> 2;                          // columns [256*half, 256*half + 256)
+    const int ch = e >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;                  // 0..255
-    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
-    constexpr bool train = TRAIN;
-    uint8_t *stg = smem_raw + OFF_STG + e * STG_WARP_BYTES;       // this warp's 4 KB staging block
-    const uint32_t stg_s = base + OFF_STG + e * STG_WARP_BYTES;
-    uint32_t ph_acc = 0;
-    int ring_pos = 0;                                 // ring slots consumed by earlier tiles
-    auto signal_aready = [&]() {                      // all 256 threads: fences done -> one arrival per CTA
-      tcgen05_fence_before();
-      named_bar_sync(1, N_EPI);
-      if (et == 0) {
-        if (rank == 0) mbar_arrive(bar.aready());
-        else mbar_arrive_remote(mapa_shared(bar.aready(), 0));
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
+    uint32_t ready_addr[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ready_addr[k] = rank == 0 ? bar.ready(k) : mapa_shared(bar.ready(k), 0);
+    // one arrival per warp: every lane has fenced its own writes, __syncwarp orders them before lane 0's release
+    auto arrive_ready = [&](int k) {
+      __syncwarp();
+      if (lane == 0) {
+        // the writes were handed to the async proxy by each lane's fence.proxy.async; the arrival itself is a signal
+        if (rank == 0) mbar_arrive(ready_addr[k]);
+        else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // chunks 4..7 of slab 1 are never read by the layer-0 MMAs but are part of the saved encoder image
-    if (half == 1)
-      for (int c8 = 4; c8 < 8; ++c8)
-        *reinterpret_cast<uint4 *>(gA + SLAB_BYTES + sw128_chunk_off(row, c8)) = make_uint4(0, 0, 0, 0);
-    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs, ring_pos += FWD_RING_PER_TILE) {
+    uint32_t ph = 0;
+    PROF_DECL(t_acc0); PROF_DECL(t_acc1); PROF_DECL(t_enc); PROF_T0(t_begin);
+    tcgen05_fence_before();
+    arrive_ready(4);                                  // D half 1 is free for the first tile
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
       const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
-      // ---- layer-0 operand: positional encoding of this row, written straight into the A image.
-      //      half 0: x and frequencies 0..4 ; half 1: bf16 residual of x, zero padding and frequencies 5..9
+      // ---- layer-0 operand: positional encoding of this row, written straight into the A image (slabs 0, 1).
+      //      ch 0: x and frequencies 0..4 ; ch 1: bf16 residual of x, zero padding and frequencies 5..9
       {
-        if (train) { if (et == 0) bulk_wait_read_all(); named_bar_sync(1, N_EPI); }
+        PROF_T0(t0);
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M) xv = p.x[m];
         const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (TRAIN) {   // the pair's bulk stores of the previous tile's last layer must have left the A image
+          if (ch == 0 && lane == 0) bulk_wait_read_all();
+          named_bar_sync(2 + q, 64);
+        }
         auto put8 = [&](int feat0, float a, float b, float c, float d) {   // 4 consecutive features (8 bytes)
           const int c8 = feat0 >> 3;
-          uint2 v = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
-          *reinterpret_cast<uint2 *>(gA + (c8 >> 3) * SLAB_BYTES + sw128_chunk_off(row, c8 & 7) + (feat0 & 7) * 2) = v;
+          *reinterpret_cast<uint2 *>(gA + (c8 >> 3) * SLAB_BYTES + sw128_chunk_off(row, c8 & 7) + (feat0 & 7) * 2) =
+              make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
         };
-        if (half == 0) {
+        if (ch == 0) {
           put8(0, xc[0], xc[1], xc[2], xc[3]);
         } else {
           float rs[4];
@@ -224,128 +281,164 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
           put8(84, rs[0], rs[1], rs[2], rs[3]);
           put8(88, 0.f, 0.f, 0.f, 0.f);
           put8(92, 0.f, 0.f, 0.f, 0.f);
+          if (TRAIN)   // features 96..127 of the saved encoder image (read by the layer-0 wgrad, never by the forward MMAs)
+            for (int c8 = 4; c8 < 8; ++c8)
+              *reinterpret_cast<uint4 *>(gA + SLAB_BYTES + sw128_chunk_off(row, c8)) = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int fi = 0; fi < 5; ++fi) {
-          const int f = half * 5 + fi;
+          const int f = ch * 5 + fi;
           float sv[4], cv[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) sincosf(xc[c] * (float)(1 << f) * 0.5f, &sv[c], &cv[c]);   // exact scalings
           put8(4 + f * 4, sv[0], sv[1], sv[2], sv[3]);
           put8(44 + f * 4, cv[0], cv[1], cv[2], cv[3]);
         }
-        fence_proxy_async_smem();
-        if (train) {
-          named_bar_sync(1, N_EPI);
-          if (et == 0) {
-            bulk_s2g(p.save_enc + (int64_t)tile * 2 * SLAB_BYTES, sA, 2 * SLAB_BYTES);
+        if (TRAIN) {   // this pair's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
+          fence_proxy_async_smem();
+          named_bar_sync(2 + q, 64);
+          if (ch == 0 && lane == 0) {
+            uint8_t *esave = p.save_enc + (int64_t)tile * 2 * SLAB_BYTES + q * PAIR_BYTES;
+            bulk_s2g(esave, sA + q * PAIR_BYTES, PAIR_BYTES);
+            bulk_s2g(esave + SLAB_BYTES, sA + SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
             bulk_commit();
           }
         }
-        signal_aready();
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        arrive_ready(0);
+        PROF_ADD(t_enc, t0);
       }
       // ---- layers
+#pragma unroll 1
       for (int l = 0; l < NH; ++l) {
-        const float2 bnext = __ldg(reinterpret_cast<const float2 *>(bias_all + l * D) + et);   // in flight during the MMAs
-        mbar_wait_cluster(bar.acc(), ph_acc); ph_acc ^= 1;
-        tcgen05_fence_after();
         const bool last = (l == NH - 1);
-        const bool write_a = !last || train;
-        if (train && et == 0) bulk_wait_read_all();   // the previous bulk store has finished reading the A image
-        reinterpret_cast<float2 *>(bias_s)[et] = bnext;
-        named_bar_sync(1, N_EPI);
-        const float *wout_s = nullptr;
-        if (last) {   // W_out pseudo-block: ring slot ring_pos + FWD_BLOCKS
-          const int slot = ring_pos + FWD_BLOCKS;
-          mbar_wait_cluster(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
-          wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
-        }
-        uint8_t *psave = train ? p.save_pre + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
+        const float *bl = bias_s + (l & 1) * D;
+        uint8_t *hsave = TRAIN ? p.save_h + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
+        uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
+        uint32_t held[64];                            // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
         float o0 = 0.f, o1 = 0.f;
-        uint32_t accA[32], accB[32];
-        tmem_ld32(tm_row, accA);
-        auto process = [&](const uint32_t (&acc)[32], int g) {
-          const int col0 = half * 256 + g * 32;
-          float hv[32];
-          uint32_t ppk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = *reinterpret_cast<const float4 *>(bias_s + col0 + i);
-            const float v0 = __uint_as_float(acc[i]) + b.x, v1 = __uint_as_float(acc[i + 1]) + b.y;
-            const float v2 = __uint_as_float(acc[i + 2]) + b.z, v3 = __uint_as_float(acc[i + 3]) + b.w;
-            hv[i] = __sinf(v0); hv[i + 1] = __sinf(v1); hv[i + 2] = __sinf(v2); hv[i + 3] = __sinf(v3);
-            if (train) { ppk[i / 2] = pack_bf16x2(v0, v1); ppk[i / 2 + 1] = pack_bf16x2(v2, v3); }
+        for (int h = 0; h < 2; ++h) {
+          {
+            PROF_T0(t0);
+            mbar_wait(bar.acc(h), ph);
+            if (h == 0) { PROF_ADD(t_acc0, t0); } else { PROF_ADD(t_acc1, t0); }
           }
-          if (last) {   // fused output layer: out = W_out h + b_out
+          tcgen05_fence_after();
+          uint32_t accA[32], accB[32];
+          tmem_ld32(tm_row + h * 256, accA);
+          if (h == 0) {
+            // every warp is past the previous layer: the other bias buffer is idle -> stage the next layer's bias
+            const int ln = (l + 1) & (NH - 1);
+            reinterpret_cast<float2 *>(bias_s + (ln & 1) * D)[et] = __ldg(reinterpret_cast<const float2 *>(bias_all + ln * D) + et);
+          } else if (!last || TRAIN) {
+            // all MMAs of layer l are complete: the A image may be overwritten with h_l, half 0 first (from registers)
+            if (TRAIN) {   // ... once the pair's bulk stores of h_{l-1} (or of the encoder image) have read it
+              if (ch == 0 && lane == 0) bulk_wait_read_all();
+              named_bar_sync(2 + q, 64);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+                    make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
+            fence_proxy_async_smem();
+            if (TRAIN) {
+              named_bar_sync(2 + q, 64);
+              if (ch == 0 && lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bulk_s2g(hsave + j * SLAB_BYTES + q * PAIR_BYTES, sA + j * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+                bulk_commit();
+              }
+            }
+            if (!last) {
+              tcgen05_fence_before();
+              arrive_ready(0);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t(&cur)[32] = (j & 1) ? accB : accA;
+            uint32_t(&nxt)[32] = (j & 1) ? accA : accB;
+            tmem_ld_wait(cur);
+            if (j + 1 < 4) tmem_ld32(tm_row + h * 256 + (j + 1) * 64, nxt);
+            const int col0 = h * 256 + j * 64 + ch * 32;
+            const int sl = h * 4 + j;
+            uint32_t pk[16], ppk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 wa = *reinterpret_cast<const float4 *>(wout_s + col0 + i);
-              const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + col0 + i);
-              o0 += hv[i] * wa.x + hv[i + 1] * wa.y + hv[i + 2] * wa.z + hv[i + 3] * wa.w;
-              o1 += hv[i] * wb.x + hv[i + 1] * wb.y + hv[i + 2] * wb.z + hv[i + 3] * wb.w;
+              const float4 b = *reinterpret_cast<const float4 *>(bl + col0 + i);
+              const float v0 = __uint_as_float(cur[i]) + b.x, v1 = __uint_as_float(cur[i + 1]) + b.y;
+              const float v2 = __uint_as_float(cur[i + 2]) + b.z, v3 = __uint_as_float(cur[i + 3]) + b.w;
+#ifdef SNF_EXP_NO_SIN
+              const float s0 = v0, s1 = v1, s2 = v2, s3 = v3;
+#else
+              const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
+#endif
+              pk[i / 2] = pack_bf16x2(s0, s1); pk[i / 2 + 1] = pack_bf16x2(s2, s3);
+              if (TRAIN) { ppk[i / 2] = pack_bf16x2(v0, v1); ppk[i / 2 + 1] = pack_bf16x2(v2, v3); }
+              if (last) {   // fused output layer: out = W_out h + b_out
+                const float4 wa = *reinterpret_cast<const float4 *>(wout_s + col0 + i);
+                const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + col0 + i);
+                o0 += s0 * wa.x + s1 * wa.y + s2 * wa.z + s3 * wa.w;
+                o1 += s0 * wb.x + s1 * wb.y + s2 * wb.z + s3 * wb.w;
+              }
             }
-          }
-          const int slab = col0 >> 6;
-          if (train && (g & 1) == 0) {   // new slab: the previous staged block must have left shared memory
-            if (lane == 0) bulk_wait_read_all();
-            __syncwarp();
-          }
+            if (TRAIN) {   // pre-activation, chunk-major layout [slab][chunk][row] x 16 B: a warp store covers 512 contiguous bytes
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int c8 = ((col0 & 63) >> 3) + c;
-            if (write_a) {
-              uint4 o;
-              o.x = pack_bf16x2(hv[c * 8 + 0], hv[c * 8 + 1]); o.y = pack_bf16x2(hv[c * 8 + 2], hv[c * 8 + 3]);
-              o.z = pack_bf16x2(hv[c * 8 + 4], hv[c * 8 + 5]); o.w = pack_bf16x2(hv[c * 8 + 6], hv[c * 8 + 7]);
-              *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c8)) = o;
+              for (int c = 0; c < 4; ++c)
+                st_stream16(psave + (((sl * 8 + 4 * ch + c) * TILE_M + row) << 4), ppk[4 * c], ppk[4 * c + 1], ppk[4 * c + 2], ppk[4 * c + 3]);
             }
-            if (train)   // pre-activation: staged per warp (32 rows x 128 B, image layout), then one 4 KB bulk store
-              *reinterpret_cast<uint4 *>(stg + sw128_chunk_off(lane, c8)) = make_uint4(ppk[c * 4], ppk[c * 4 + 1], ppk[c * 4 + 2], ppk[c * 4 + 3]);
-          }
-          if (train && (g & 1) == 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              bulk_s2g(psave + slab * SLAB_BYTES + (q * 32) * 128, stg_s, STG_WARP_BYTES);
-              bulk_commit();
+            if (!last || TRAIN) {
+              if (h == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) held[16 * j + k] = pk[k];
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+                      make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                fence_proxy_async_smem();
+                if (TRAIN) {   // h_l for the weight gradients: the pair's 32 rows of this slab are one contiguous 4 KB block
+                  named_bar_sync(2 + q, 64);
+                  if (ch == 0 && lane == 0) {
+                    bulk_s2g(hsave + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+                    bulk_commit();
+                  }
+                }
+                if (!last) {
+                  tcgen05_fence_before();
+                  arrive_ready(1 + j);
+                }
+              }
             }
-          }
-        };
-#pragma unroll 1
-        for (int g = 0; g < 8; g += 2) {   // software-pipelined TMEM reads: the next group loads while this one computes
-          tmem_ld_wait(accA);
-          tmem_ld32(tm_row + (g + 1) * 32, accB);
-          process(accA, g);
-          tmem_ld_wait(accB);
-          if (g + 2 < 8) tmem_ld32(tm_row + (g + 2) * 32, accA);
-          process(accB, g + 1);
-        }
-        if (write_a) fence_proxy_async_smem();
-        if (train) {
-          named_bar_sync(1, N_EPI);
-          if (et == 0) {
-            uint8_t *dst = p.save_h + ((int64_t)tile * NH + l) * A_BYTES;
-#pragma unroll 1
-            for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
-            bulk_commit();
           }
         }
+        ph ^= 1;
         if (last) {
-          // combine the two column halves of each row through the (now idle) bias buffer, release the W_out slot
+          tcgen05_fence_before();
+          arrive_ready(4);                            // D half 1 drained: the next tile's layer 0 may use it
+          // combine the two column groups of each row
+          if (ch == 1) osum_s[row] = make_float2(o0, o1);
           named_bar_sync(1, N_EPI);
-          if (et == 0) mbar_arrive(bar.empty((ring_pos + FWD_BLOCKS) % NSTAGE));
-          if (half == 1) reinterpret_cast<float2 *>(bias_s)[row] = make_float2(o0, o1);
-          named_bar_sync(1, N_EPI);
-          if (half == 0 && m < p.M) {
-            const float2 o = reinterpret_cast<const float2 *>(bias_s)[row];
+          if (ch == 0 && m < p.M) {
+            const float2 o = osum_s[row];
             p.out[m] = make_float2((o0 + o.x) + __ldg(b_out) + p.off0, (o1 + o.y) + __ldg(b_out + 1) + p.off1);
           }
-        } else {
-          signal_aready();
         }
       }
     }
-    if (train && lane == 0) bulk_wait_all();
+    if (TRAIN && ch == 0 && lane == 0) bulk_wait_all();
+#ifdef SNF_PROF
+    if (e == 0 && lane == 0) {
+      g_prof[TRAIN][blockIdx.x * 8 + 3] = clock64() - t_begin;
+      g_prof[TRAIN][blockIdx.x * 8 + 4] = t_acc0;
+      g_prof[TRAIN][blockIdx.x * 8 + 5] = t_acc1;
+      g_prof[TRAIN][blockIdx.x * 8 + 6] = t_enc;
+    }
+#endif
   }
   tcgen05_fence_before();
   cluster_sync_all();
@@ -363,6 +456,18 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
                       float *const *gB, int num_sms, cudaStream_t st);
 
 int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train) { return bf::bf16_layout(nullptr, M, train).bytes; }
+
+#ifdef SNF_PROF
+// debug build only: per-CTA cycle counters of the last forward launches ([0] inference, [1] training)
+extern "C" int snf_debug_prof(unsigned long long *host) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, bf::g_prof, sizeof(bf::g_prof));
+}
+extern "C" int snf_debug_trace(long long *host) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, bf::g_trace, sizeof(bf::g_trace));
+}
+#endif
 
 extern "C" int64_t snf_mlp_pack_bytes(void) { return bf::PACK_TOTAL_BYTES; }
 
@@ -400,9 +505,9 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   if (train) { SNF_CHECK_PTR(ws); SNF_CHECK_ALIGN(ws, 1024); }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -420,8 +525,8 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   grid &= ~1;   // whole CTA pairs
-  if (train) bf::mlp_fwd_bf16_kernel<true><<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
-  else bf::mlp_fwd_bf16_kernel<false><<<grid, bf::NTHREADS, bf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  if (train) bf::mlp_fwd_bf16_kernel<true><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  else bf::mlp_fwd_bf16_kernel<false><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   count_launch();
   return launch_status();
 }

@@ -81,13 +81,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-        mbar_wait_cluster(bar.empty(s), ph ^ 1);
+        mbar_wait(bar.empty(s), ph ^ 1);
         mbar_arrive_expect_tx(bar.full(s), WOUT_BYTES);
         bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
         if (++s == NSTAGE) { s = 0; ph ^= 1; }
         for (int l = NH - 1; l >= 1; --l)
           for (int b = 0; b < 16; ++b) {
-            mbar_wait_cluster(bar.empty(s), ph ^ 1);
+            mbar_wait(bar.empty(s), ph ^ 1);
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
             bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -102,11 +102,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
           if (++s == NSTAGE) { s = 0; ph ^= 1; }        // W_out pseudo-block: consumed by the epilogue warps
           for (int l = NH - 1; l >= 1; --l) {
-            mbar_wait_cluster(bar.aready(), ph_a); ph_a ^= 1;
+            mbar_wait(bar.aready(), ph_a); ph_a ^= 1;
             tcgen05_fence_after();
             for (int q = 0; q < 2; ++q)
               for (int ks = 0; ks < 8; ++ks) {
-                mbar_wait_cluster(bar.full(s), ph);
+                mbar_wait(bar.full(s), ph);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
@@ -125,7 +125,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
           for (int blk = 0; blk < DG_RING_PER_TILE; ++blk) {
             mbar_wait(bar.full(s), ph);
-            mbar_arrive_remote(mapa_shared(bar.full(s), 0));
+            mbar_arrive_remote_relaxed(mapa_shared(bar.full(s), 0));   // the data is TMA-written and tensor-core-read
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
         }
@@ -147,20 +147,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         else mbar_arrive_remote(mapa_shared(bar.aready(), 0));
       }
     };
-    // coalesced fetch of this warp's 32 rows of one pre-activation slab (4 KB, contiguous in the image) into staging
-    auto fetch_slab = [&](const uint8_t *img, int slab) {
-      const uint8_t *src = img + slab * SLAB_BYTES + (q * 32) * 128;
+    // this thread's row of one pre-activation slab: 8 chunks of 8 bf16 in the chunk-major layout the forward wrote
+    // ([slab][chunk][row] x 16 B: a warp load covers 512 contiguous bytes)
+    auto load_row = [&](const uint8_t *img, int slab, uint4 (&pv)[8]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cp_async16(stg_s + i * 512 + lane * 16, src + i * 512 + lane * 16);
-      cp_async_commit();
-    };
-    // this thread's row of the staged slab: 8 chunks of 8 bf16 (logical order)
-    auto read_row = [&](uint4 (&pv)[8]) {
-      cp_async_wait_all();
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 8; ++c) pv[c] = *reinterpret_cast<const uint4 *>(stg + sw128_chunk_off(lane, c));
-      __syncwarp();                                   // everyone has read: staging may be refilled
+      for (int c = 0; c < 8; ++c)
+        pv[c] = __ldcs(reinterpret_cast<const uint4 *>(img + (((slab * 8 + c) * TILE_M + row) << 4)));
     };
     for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs, ring_pos += DG_RING_PER_TILE) {
       const int tile = tp * 2 + (int)rank;
@@ -170,20 +162,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7)
       {
         const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
-        fetch_slab(p7, half * 4);
+        uint4 pn[8];
+        load_row(p7, half * 4, pn);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
         if (et == 0) bulk_wait_read_all();            // previous tile's last bulk store has left the A image
         named_bar_sync(1, N_EPI);
         const int slot = ring_pos;                    // W_out pseudo-block
-        mbar_wait_cluster(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
+        mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
         const float *wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int slab = half * 4 + j;
           uint4 pv[8];
-          read_row(pv);
-          if (j + 1 < 4) fetch_slab(p7, slab + 1);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pv[c] = pn[c];
+          if (j + 1 < 4) load_row(p7, slab + 1, pn);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int col = slab * 64 + c * 8;
@@ -211,8 +205,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       for (int l = NH - 1; l >= 1; --l) {
         // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos(pre_{l-1}) -> dpre_{l-1}
         const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * A_BYTES;
-        fetch_slab(pprev, half * 4);                  // in flight during the MMAs
-        mbar_wait_cluster(bar.acc(), ph_acc); ph_acc ^= 1;
+        uint4 pn[8];
+        load_row(pprev, half * 4, pn);                // in flight during the MMAs
+        mbar_wait(bar.acc(), ph_acc); ph_acc ^= 1;
         tcgen05_fence_after();
         if (et == 0) bulk_wait_read_all();
         named_bar_sync(1, N_EPI);
@@ -234,8 +229,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         for (int j = 0; j < 4; ++j) {
           const int slab = half * 4 + j;
           uint4 pv[8];
-          read_row(pv);
-          if (j + 1 < 4) fetch_slab(pprev, slab + 1);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pv[c] = pn[c];
+          if (j + 1 < 4) load_row(pprev, slab + 1, pn);
           tmem_ld_wait(accA);
           tmem_ld32(tm_row + (2 * j + 1) * 32, accB);
           process(accA, pv, slab, 0);
