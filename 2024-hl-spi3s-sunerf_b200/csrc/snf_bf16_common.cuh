@@ -23,7 +23,9 @@ constexpr int NSTAGE_INFER = 6;              // inference needs no staging: deep
 constexpr int NSTAGE_MAX = 6;
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_EPI = N_EPI_WARPS * 32;      // 256 epilogue threads: (row, column half)
-constexpr int NTHREADS = 64 + N_EPI;         // warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2..9 epilogue
+constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2-3 idle;
+constexpr int NTHREADS = 128 + N_EPI;        // warpgroups 1-2 (warps 4..11): epilogue.  Registers are re-balanced with setmaxnreg:
+constexpr int REGS_CTRL = 40, REGS_EPI = 232;   // per SM sub-partition 1 control warp + 2 epilogue warps: 40 + 2 x 232 <= 512
 constexpr int STG_WARP_BYTES = 32 * 128;     // per-warp staging: 32 rows of one 64-column slab = 4 KB (contiguous in an image)
 constexpr int STG_BYTES = N_EPI_WARPS * STG_WARP_BYTES;
 constexpr int BIAS_BYTES = D * 4;

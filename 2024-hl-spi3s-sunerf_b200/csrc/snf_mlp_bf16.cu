@@ -135,6 +135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::TMEM_SLOT_OFF);
 
+  if (warp < EPI_WARP0) {
+  reg_dealloc<REGS_CTRL>();
   if (warp == 0) {
     // =========================== TMA producer (each CTA streams its half of every weight block)
     if (lane == 0) {
@@ -228,14 +230,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         }
       }
     }
+  }
   } else {
+    reg_alloc<REGS_EPI>();
     // =========================== epilogue warps: 256 threads.  Thread = (row, ch): in temporal half h, step j it owns
     // the 32 accumulator columns 256h + 64j + 32ch .. +31, i.e. chunks 4ch..4ch+3 of A slab 4h + j.
-    const int e = warp - 2;
+    const int e = warp - EPI_WARP0;
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     const int ch = e >> 2;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;                  // 0..255
+    const int et = threadIdx.x - EPI_WARP0 * 32;                  // 0..255
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
     uint32_t ready_addr[5];
 #pragma unroll

@@ -47,140 +47,175 @@ struct DgradParams {
   int64_t M;
   int num_tiles;            // even
   const uint8_t *packed;    // forward pack + W^T blocks
-  const uint8_t *save_pre;  // [tiles][8][128 KB] pre-activation images
+  const uint8_t *save_pre;  // [tiles][8][128 KB] pre-activations, chunk-major layout (snf_mlp_bf16.cu)
   uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
-constexpr int DG_RING_PER_TILE = 1 + WT_BLOCKS;   // W_out pseudo-block, then 7 layers x 16 W^T blocks
-constexpr int NSTAGE = NSTAGE_TRAIN;              // the staging area is used for the coalesced pre-activation fetches
+constexpr int PAIR_BYTES = 32 * 128;   // 32 rows of one slab: what the two warps of a TMEM lane quarter own (4 KB, contiguous)
 
+__device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// Same overlapped structure as the forward (snf_mlp_bf16.cu): per layer two temporal N-halves, the epilogue of half 0
+// runs under the MMAs of half 1 and keeps its result in registers until the A image may be overwritten; the next
+// layer's MMAs start slab by slab.  Shared-memory layout and barriers: namespace fw (the bias area is unused).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
+  constexpr int NSTAGE = fw::NSTAGE, OFF_RING = fw::OFF_RING, OFF_WOUT = fw::OFF_WOUT, OFF_BAR = fw::OFF_BAR;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
   uint8_t *gA = smem_raw;
   const uint32_t sA = base, sW = base + OFF_RING;
-  const Bars bar{base + OFF_BAR};
+  float *wout_s = reinterpret_cast<float *>(smem_raw + OFF_WOUT);          // [2][512]
+  const fw::Bars bar{base + OFF_BAR};
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
-    mbar_init(bar.acc(), 1);
-    mbar_init(bar.aready(), 2);
+    mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
+    for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
   if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + TMEM_SLOT_OFF);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::TMEM_SLOT_OFF);
   const uint8_t *wt = p.packed + PACK_WT_OFF;
 
+  if (warp < EPI_WARP0) {
+  reg_dealloc<REGS_CTRL>();
   if (warp == 0) {
+    // =========================== TMA producer: W^T blocks through the ring, plus L2 prefetches of the saved
+    // pre-activation images about one layer ahead of the epilogue that multiplies by their cosine
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      auto pre_img = [&](int tile, int l) { return p.save_pre + ((int64_t)tile * NH + l) * A_BYTES; };
+      {
+        const int tile = pair * 2 + (int)rank;
+        if (tile < p.num_tiles)
+          for (int sl = 0; sl < 8; ++sl) {
+            prefetch_l2(pre_img(tile, NH - 1) + sl * SLAB_BYTES, SLAB_BYTES);
+            prefetch_l2(pre_img(tile, NH - 2) + sl * SLAB_BYTES, SLAB_BYTES);
+          }
+      }
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-        mbar_wait(bar.empty(s), ph ^ 1);
-        mbar_arrive_expect_tx(bar.full(s), WOUT_BYTES);
-        bulk_g2s(sW + s * WHALF_BYTES, p.packed + PACK_WOUT_OFF, WOUT_BYTES, bar.full(s));
-        if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        const int tile = tp * 2 + (int)rank, next_tile = tile + 2 * npairs;
         for (int l = NH - 1; l >= 1; --l)
           for (int b = 0; b < 16; ++b) {
             mbar_wait(bar.empty(s), ph ^ 1);
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
             bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
+            if (l >= 2) {
+              if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * SLAB_BYTES, SLAB_BYTES);
+            } else if (next_tile < p.num_tiles) {   // l == 1: the next tile's first two images
+              prefetch_l2(pre_img(next_tile, b < 8 ? NH - 1 : NH - 2) + (b & 7) * SLAB_BYTES, SLAB_BYTES);
+            }
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0, ph_a = 0;
-      if (rank == 0) {
-        const uint32_t idesc = idesc_bf16(256, NCHUNK);
-        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }        // W_out pseudo-block: consumed by the epilogue warps
-          for (int l = NH - 1; l >= 1; --l) {
-            mbar_wait(bar.aready(), ph_a); ph_a ^= 1;
-            tcgen05_fence_after();
-            for (int q = 0; q < 2; ++q)
-              for (int ks = 0; ks < 8; ++ks) {
-                mbar_wait(bar.full(s), ph);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const uint64_t ad = smem_desc(sA + ks * SLAB_BYTES + k4 * 32, 16, 1024);
-                  const uint64_t bd = smem_desc(sW + s * WHALF_BYTES + k4 * 32, 16, 1024);
-                  mma_ss_2cta(tmem + q * NCHUNK, ad, bd, idesc, (ks | k4) != 0);
-                }
-                mma_commit_2cta(bar.empty(s), 3);
-                if (++s == NSTAGE) { s = 0; ph ^= 1; }
+    int s = 0; uint32_t ph = 0;
+    if (rank == 0) {
+      // =========================== MMA issuer (leader CTA); see the forward kernel
+      const uint32_t idesc = idesc_bf16(256, NCHUNK);
+      const uint64_t adesc0 = smem_desc(sA, 16, 1024), bdesc0 = smem_desc(sW, 16, 1024);
+      uint32_t rph = 0;
+      auto wait_ready = [&](int k) { mbar_wait(bar.ready(k), (rph >> k) & 1u); rph ^= 1u << k; };
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+        for (int l = NH - 1; l >= 1; --l) {
+          for (int h = 0; h < 2; ++h) {
+            for (int ks = 0; ks < 8; ++ks) {
+              if (h == 0) {
+                if (ks == 0) wait_ready(0);
+                else if (ks >= 4) wait_ready(ks - 3);
               }
-            mma_commit_2cta(bar.acc(), 3);
+              mbar_wait(bar.full(s), ph);
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = adesc0 + (uint64_t)((ks * SLAB_BYTES) >> 4), bd = bdesc0 + (uint64_t)((s * WHALF_BYTES) >> 4);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (ks | k4) != 0);
+                mma_commit_2cta(bar.empty(s), 3);
+                if (ks == 7) mma_commit_2cta(bar.acc(h), 3);
+              }
+              __syncwarp();
+              if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            }
           }
         }
-      } else {
-        // every ring slot is relayed (the W_out pseudo-block too) so the leader's full[s] keeps the ring's phase
-        for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-          for (int blk = 0; blk < DG_RING_PER_TILE; ++blk) {
-            mbar_wait(bar.full(s), ph);
-            mbar_arrive_remote_relaxed(mapa_shared(bar.full(s), 0));   // the data is TMA-written and tensor-core-read
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
-          }
+      }
+    } else if (lane == 0) {
+      for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+        for (int blk = 0; blk < WT_BLOCKS; ++blk) {
+          mbar_wait(bar.full(s), ph);
+          mbar_arrive_remote_relaxed(mapa_shared(bar.full(s), 0));   // the data is TMA-written and tensor-core-read
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
+  }
   } else {
-    // epilogue warps: thread = (row, column half); 4 slabs (2 groups of 32 columns each) per thread and layer
-    const int e = warp - 2, q = warp & 3, half = e >> 2, row = q * 32 + lane, et = threadIdx.x - 64;
-    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + half * 256;
-    uint8_t *stg = smem_raw + OFF_STG + e * STG_WARP_BYTES;
-    const uint32_t stg_s = base + OFF_STG + e * STG_WARP_BYTES;
-    uint32_t ph_acc = 0;
-    int ring_pos = 0;
-    auto signal_aready = [&]() {
-      tcgen05_fence_before();
-      named_bar_sync(1, N_EPI);
-      if (et == 0) {
-        if (rank == 0) mbar_arrive(bar.aready());
-        else mbar_arrive_remote(mapa_shared(bar.aready(), 0));
+    reg_alloc<REGS_EPI>();
+    // =========================== epilogue warps: thread = (row, ch); step (h, j) <-> slab 4h + j, chunks 4ch..4ch+3
+    const int e = warp - EPI_WARP0, q = warp & 3, ch = e >> 2, row = q * 32 + lane;
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
+    uint32_t ready_addr[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ready_addr[k] = rank == 0 ? bar.ready(k) : mapa_shared(bar.ready(k), 0);
+    auto arrive_ready = [&](int k) {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(ready_addr[k]);
+        else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // this thread's row of one pre-activation slab: 8 chunks of 8 bf16 in the chunk-major layout the forward wrote
-    // ([slab][chunk][row] x 16 B: a warp load covers 512 contiguous bytes)
-    auto load_row = [&](const uint8_t *img, int slab, uint4 (&pv)[8]) {
+    // this thread's 32 pre-activations of one step: 4 chunks of 8 bf16 in the chunk-major layout
+    auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[4]) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        pv[c] = __ldcs(reinterpret_cast<const uint4 *>(img + (((slab * 8 + c) * TILE_M + row) << 4)));
+      for (int c = 0; c < 4; ++c)
+        pv[c] = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 8 + 4 * ch + c) * TILE_M + row) << 4)));
     };
-    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs, ring_pos += DG_RING_PER_TILE) {
+    // slab sl of the A image is complete for this pair's 32 rows: hand it to the MMAs and store it for the wgrad
+    auto publish = [&](uint8_t *dimg, int sl0, int nsl) {
+      fence_proxy_async_smem();
+      named_bar_sync(2 + q, 64);
+      if (ch == 0 && lane == 0) {
+        for (int sl = sl0; sl < sl0 + nsl; ++sl)
+          bulk_s2g(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+        bulk_commit();
+      }
+    };
+    uint32_t ph = 0;
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
       const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
       const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * A_BYTES;
       uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
-      // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7)
+      uint4 pn[4];
+      // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7), written straight into the A image
       {
         const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
-        uint4 pn[8];
-        load_row(p7, half * 4, pn);
+        uint8_t *d7 = d_tile + (int64_t)(NH - 1) * A_BYTES;
+        load_pre(p7, 0, pn);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
-        if (et == 0) bulk_wait_read_all();            // previous tile's last bulk store has left the A image
-        named_bar_sync(1, N_EPI);
-        const int slot = ring_pos;                    // W_out pseudo-block
-        mbar_wait(bar.full(slot % NSTAGE), (uint32_t)((slot / NSTAGE) & 1));
-        const float *wout_s = reinterpret_cast<const float *>(smem_raw + OFF_RING + (slot % NSTAGE) * WHALF_BYTES);
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int slab = half * 4 + j;
-          uint4 pv[8];
+        if (ch == 0 && lane == 0) bulk_wait_read_all();   // the previous tile's last stores have left the A image
+        named_bar_sync(2 + q, 64);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) pv[c] = pn[c];
-          if (j + 1 < 4) load_row(p7, slab + 1, pn);
+        for (int sl = 0; sl < 8; ++sl) {
+          uint4 pv[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int col = slab * 64 + c * 8;
+          for (int c = 0; c < 4; ++c) pv[c] = pn[c];
+          if (sl + 1 < 8) load_pre(p7, sl + 1, pn);
+          else load_pre(pre_tile + (int64_t)(NH - 2) * A_BYTES, 0, pn);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = sl * 64 + (4 * ch + c) * 8;
             const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col), wa1 = *reinterpret_cast<const float4 *>(wout_s + col + 4);
             const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col + 4);
             uint4 o;
@@ -188,69 +223,84 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * __cosf(bf_lo(pv[c].y)), (gg.x * wa0.w + gg.y * wb0.w) * __cosf(bf_hi(pv[c].y)));
             o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * __cosf(bf_lo(pv[c].z)), (gg.x * wa1.y + gg.y * wb1.y) * __cosf(bf_hi(pv[c].z)));
             o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * __cosf(bf_lo(pv[c].w)), (gg.x * wa1.w + gg.y * wb1.w) * __cosf(bf_hi(pv[c].w)));
-            *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c)) = o;
+            *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) = o;
           }
+          publish(d7, sl, 1);
+          tcgen05_fence_before();
+          if (sl == 3) arrive_ready(0);
+          if (sl >= 4) arrive_ready(sl - 3);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, N_EPI);
-        if (et == 0) {
-          mbar_arrive(bar.empty(slot % NSTAGE));      // W_out slot back to the producer
-          uint8_t *dst = d_tile + (int64_t)(NH - 1) * A_BYTES;
-#pragma unroll 1
-          for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
-          bulk_commit();
-        }
-        signal_aready();
       }
+#pragma unroll 1
       for (int l = NH - 1; l >= 1; --l) {
         // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos(pre_{l-1}) -> dpre_{l-1}
+        const bool last = (l == 1);
         const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * A_BYTES;
-        uint4 pn[8];
-        load_row(pprev, half * 4, pn);                // in flight during the MMAs
-        mbar_wait(bar.acc(), ph_acc); ph_acc ^= 1;
-        tcgen05_fence_after();
-        if (et == 0) bulk_wait_read_all();
-        named_bar_sync(1, N_EPI);
-        uint32_t accA[32], accB[32];
-        tmem_ld32(tm_row, accA);
-        auto process = [&](const uint32_t (&acc)[32], const uint4 *pv, int slab, int c0) {
+        const uint8_t *pnext = pre_tile + (int64_t)(l >= 2 ? l - 2 : 0) * A_BYTES;
+        uint8_t *dprev = d_tile + (int64_t)(l - 1) * A_BYTES;
+        uint32_t held[64];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 pw = pv[c];
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(acc[c * 8 + 0]) * __cosf(bf_lo(pw.x)), __uint_as_float(acc[c * 8 + 1]) * __cosf(bf_hi(pw.x)));
-            o.y = pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * __cosf(bf_lo(pw.y)), __uint_as_float(acc[c * 8 + 3]) * __cosf(bf_hi(pw.y)));
-            o.z = pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * __cosf(bf_lo(pw.z)), __uint_as_float(acc[c * 8 + 5]) * __cosf(bf_hi(pw.z)));
-            o.w = pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * __cosf(bf_lo(pw.w)), __uint_as_float(acc[c * 8 + 7]) * __cosf(bf_hi(pw.w)));
-            *reinterpret_cast<uint4 *>(gA + slab * SLAB_BYTES + sw128_chunk_off(row, c0 + c)) = o;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar.acc(h), ph);
+          tcgen05_fence_after();
+          uint32_t accA[16], accB[16];                // 16-column TMEM loads, double buffered
+          tmem_ld16(tm_row + h * 256, accA);
+          if (h == 1) {
+            // all MMAs of layer l are complete: the A image may be overwritten with dpre_{l-1}, half 0 from registers
+            if (ch == 0 && lane == 0) bulk_wait_read_all();   // ... once the stores of dpre_l have read it
+            named_bar_sync(2 + q, 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+                    make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
+            publish(dprev, 0, 4);
+            if (!last) { tcgen05_fence_before(); arrive_ready(0); }
           }
-        };
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int slab = half * 4 + j;
-          uint4 pv[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) pv[c] = pn[c];
-          if (j + 1 < 4) load_row(pprev, slab + 1, pn);
-          tmem_ld_wait(accA);
-          tmem_ld32(tm_row + (2 * j + 1) * 32, accB);
-          process(accA, pv, slab, 0);
-          tmem_ld_wait(accB);
-          if (j + 1 < 4) tmem_ld32(tm_row + (2 * j + 2) * 32, accA);
-          process(accB, pv + 4, slab, 4);
+          for (int j = 0; j < 4; ++j) {
+            const int sl = h * 4 + j;
+            uint4 pv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pv[c] = pn[c];
+            if (sl + 1 < 8) load_pre(pprev, sl + 1, pn);
+            else if (!last) load_pre(pnext, 0, pn);
+            uint32_t pk[16];
+            auto half_step = [&](const uint32_t (&a)[16], int c0) {   // 16 columns = chunks c0, c0 + 1 of this step
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const uint4 pw = pv[c0 + c];
+                pk[4 * (c0 + c) + 0] = pack_bf16x2(__uint_as_float(a[c * 8 + 0]) * __cosf(bf_lo(pw.x)), __uint_as_float(a[c * 8 + 1]) * __cosf(bf_hi(pw.x)));
+                pk[4 * (c0 + c) + 1] = pack_bf16x2(__uint_as_float(a[c * 8 + 2]) * __cosf(bf_lo(pw.y)), __uint_as_float(a[c * 8 + 3]) * __cosf(bf_hi(pw.y)));
+                pk[4 * (c0 + c) + 2] = pack_bf16x2(__uint_as_float(a[c * 8 + 4]) * __cosf(bf_lo(pw.z)), __uint_as_float(a[c * 8 + 5]) * __cosf(bf_hi(pw.z)));
+                pk[4 * (c0 + c) + 3] = pack_bf16x2(__uint_as_float(a[c * 8 + 6]) * __cosf(bf_lo(pw.w)), __uint_as_float(a[c * 8 + 7]) * __cosf(bf_hi(pw.w)));
+              }
+            };
+            tmem_ld_wait(accA);
+            tmem_ld16(tm_row + h * 256 + j * 64 + 16, accB);
+            half_step(accA, 0);
+            tmem_ld_wait(accB);
+            if (j + 1 < 4) tmem_ld16(tm_row + h * 256 + (j + 1) * 64, accA);
+            half_step(accB, 2);
+            if (h == 0) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) held[16 * j + k] = pk[k];
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+              publish(dprev, sl, 1);
+              tcgen05_fence_before();
+              if (!last) arrive_ready(1 + j);
+            }
+          }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, N_EPI);
-        if (et == 0) {
-          uint8_t *dst = d_tile + (int64_t)(l - 1) * A_BYTES;
-#pragma unroll 1
-          for (int sl = 0; sl < 8; ++sl) bulk_s2g(dst + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES);
-          bulk_commit();
-        }
-        if (l > 1) signal_aready();
+        ph ^= 1;
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (ch == 0 && lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   cluster_sync_all();
@@ -479,7 +529,7 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
                       float *const *gB, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(bf::mlp_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::WG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -500,7 +550,7 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   dp.save_pre = w.pre; dp.save_d = w.d;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   grid &= ~1;
-  bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(dp);
+  bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, st>>>(dp);
   if (int e = debug_sync("mlp_dgrad_bf16_kernel", st)) return e;
 
   bf::WgradParams wp{};
