@@ -308,11 +308,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
+// CTA pairs (tcgen05 cta_group::2, M = 256 output features across the pair, N = 256 input features per instruction):
+// CTA r of a pair owns output features [256 ob + 128 r, +128) - its A operand (2 slabs of D_l) and its 128 x 512 fp32
+// accumulator (all of its TMEM) - and supplies half of every B operand (2 of the 4 H slabs of each N = 256
+// instruction), so a pipeline stage of 32 points is 24 KB per CTA instead of the 40 KB a single-CTA tile needs.
 constexpr int WG_KSTAGE = 32;                           // points per pipeline stage
 constexpr int WG_SLAB_STAGE = WG_KSTAGE * 128;          // 4 KB: 32 rows of one 64-feature slab
-constexpr int WG_STAGE_BYTES = 10 * WG_SLAB_STAGE;      // 2 (o-block) + 8 (all i) slabs = 40 KB
-constexpr int WG_NSTAGE = 5;
+constexpr int WG_STAGE_BYTES = 6 * WG_SLAB_STAGE;       // 2 (own o) + 2 x 2 (own half of i, two N-halves) slabs = 24 KB
+constexpr int WG_NSTAGE = 9;
 constexpr int WG_SMEM_BYTES = WG_NSTAGE * WG_STAGE_BYTES + 256;
+static_assert(WG_SMEM_BYTES <= 232448, "wgrad ring exceeds shared memory");
 
 struct WgradParams {
   const uint8_t *save_d, *save_h, *save_enc;
@@ -325,35 +330,37 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const WgradParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
   uint8_t *gS = smem_raw;
   const uint32_t sBar = base + WG_NSTAGE * WG_STAGE_BYTES;
-  auto bar_full = [&](int s) { return sBar + 8u * s; };
-  auto bar_empty = [&](int s) { return sBar + 8u * (WG_NSTAGE + s); };
-  const uint32_t bar_acc = sBar + 8u * (2 * WG_NSTAGE), bar_accfree = sBar + 8u * (2 * WG_NSTAGE + 1);
+  auto bar_full = [&](int s) { return sBar + 8u * s; };                       // leader: own TMA + peer relay
+  auto bar_empty = [&](int s) { return sBar + 8u * (WG_NSTAGE + s); };       // multicast commit + this CTA's 4 bias warps
+  const uint32_t bar_acc = sBar + 8u * (2 * WG_NSTAGE);                      // item accumulated (multicast commit)
+  const uint32_t bar_accfree = sBar + 8u * (2 * WG_NSTAGE + 1);              // leader: 8 flush warps (both CTAs) done
   const uint32_t tmem_slot = sBar + 8u * (2 * WG_NSTAGE + 2);
   volatile uint32_t *tmem_slot_g = reinterpret_cast<volatile uint32_t *>(gS + WG_NSTAGE * WG_STAGE_BYTES + 8 * (2 * WG_NSTAGE + 2));
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 4); }
+    for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1 + 4); }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 128);
+    mbar_init(bar_accfree, 8);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot_g;
 
-  // item -> (tile range, layer, o-block); the 4 o-blocks of one (range, layer) are adjacent so that CTAs running
-  // side by side share the Hprev tiles in L2
+  // item -> (tile range, layer, 256-wide o-block)
   auto decode = [&](int item, int &l, int &ob, int &t0, int &t1) {
-    ob = item & 3; l = (item >> 2) & 7;
-    const int r = item >> 5;
+    ob = item & 1; l = (item >> 1) & 7;
+    const int r = item >> 4;
     t0 = r * p.tiles_per_item;
     t1 = min(t0 + p.tiles_per_item, p.num_tiles);
   };
@@ -361,11 +368,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const Wgr
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = pair; item < p.num_items; item += npairs) {
         int l, ob, t0, t1; decode(item, l, ob, t0, t1);
-        const int nb = l == 0 ? 2 : 8;
+        const int nb = l == 0 ? 1 : 4;
         for (int t = t0; t < t1; ++t) {
-          const uint8_t *dimg = p.save_d + ((int64_t)t * NH + l) * A_BYTES + (int64_t)ob * 2 * SLAB_BYTES;
+          const uint8_t *dimg = p.save_d + ((int64_t)t * NH + l) * A_BYTES + (int64_t)(ob * 4 + rank * 2) * SLAB_BYTES;
           const uint8_t *himg = l == 0 ? p.save_enc + (int64_t)t * 2 * SLAB_BYTES
                                        : p.save_h + ((int64_t)t * NH + (l - 1)) * A_BYTES;
           for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
@@ -374,19 +381,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const Wgr
             const uint32_t st = base + s * WG_STAGE_BYTES;
             for (int j = 0; j < 2; ++j)
               bulk_g2s(st + j * WG_SLAB_STAGE, dimg + j * SLAB_BYTES + qd * WG_SLAB_STAGE, WG_SLAB_STAGE, bar_full(s));
-            for (int j = 0; j < nb; ++j)
-              bulk_g2s(st + (2 + j) * WG_SLAB_STAGE, himg + j * SLAB_BYTES + qd * WG_SLAB_STAGE, WG_SLAB_STAGE, bar_full(s));
+            if (l == 0) {
+              bulk_g2s(st + 2 * WG_SLAB_STAGE, himg + rank * SLAB_BYTES + qd * WG_SLAB_STAGE, WG_SLAB_STAGE, bar_full(s));
+            } else {
+              for (int nh = 0; nh < 2; ++nh)
+                for (int j = 0; j < 2; ++j)
+                  bulk_g2s(st + (2 + nh * 2 + j) * WG_SLAB_STAGE, himg + (nh * 4 + rank * 2 + j) * SLAB_BYTES + qd * WG_SLAB_STAGE,
+                           WG_SLAB_STAGE, bar_full(s));
+            }
             if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc256 = idesc_bf16(128, 256, 1, 1), idesc128 = idesc_bf16(128, 128, 1, 1);
-      int s = 0; uint32_t ph = 0, ph_free = 0;
+    int s = 0; uint32_t ph = 0;
+    if (rank == 0) {
+      // MMA issuer: the whole warp runs the uniform control flow, one elected lane issues
+      const uint32_t idesc256 = idesc_bf16(256, 256, 1, 1), idesc128 = idesc_bf16(256, 128, 1, 1);
+      const uint64_t desc0 = smem_desc(base, WG_SLAB_STAGE, 1024);   // MN-major: LBO = slab stride in the stage, SBO = 8-point groups
+      uint32_t ph_free = 0;
       bool first_item = true;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = pair; item < p.num_items; item += npairs) {
         int l, ob, t0, t1; decode(item, l, ob, t0, t1);
         if (!first_item) { mbar_wait(bar_accfree, ph_free); ph_free ^= 1; tcgen05_fence_after(); }
         first_item = false;
@@ -395,37 +411,48 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const Wgr
           for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
             mbar_wait(bar_full(s), ph);
             tcgen05_fence_after();
-            const uint32_t st = base + s * WG_STAGE_BYTES;
+            if (elect_one()) {
+              const uint64_t sd = desc0 + (uint64_t)((s * WG_STAGE_BYTES) >> 4);
 #pragma unroll
-            for (int k16 = 0; k16 < WG_KSTAGE / 16; ++k16) {
-              // MN-major operands: LBO = stride between 64-feature slabs inside the stage, SBO = 8-point groups
-              const uint64_t ad = smem_desc(st + k16 * 2048, WG_SLAB_STAGE, 1024);
-              if (l == 0) {
-                const uint64_t bd = smem_desc(st + 2 * WG_SLAB_STAGE + k16 * 2048, WG_SLAB_STAGE, 1024);
-                mma_ss(tmem, ad, bd, idesc128, accumulate);
-              } else {
+              for (int k16 = 0; k16 < WG_KSTAGE / 16; ++k16) {
+                const uint64_t ad = sd + (uint64_t)((k16 * 2048) >> 4);
+                if (l == 0) {
+                  mma_ss_2cta(tmem, ad, ad + (uint64_t)((2 * WG_SLAB_STAGE) >> 4), idesc128, accumulate | k16);
+                } else {
 #pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
-                  const uint64_t bd = smem_desc(st + (2 + nh * 4) * WG_SLAB_STAGE + k16 * 2048, WG_SLAB_STAGE, 1024);
-                  mma_ss(tmem + nh * 256, ad, bd, idesc256, accumulate);
+                  for (int nh = 0; nh < 2; ++nh)
+                    mma_ss_2cta(tmem + nh * 256, ad, ad + (uint64_t)(((2 + nh * 2) * WG_SLAB_STAGE) >> 4), idesc256, accumulate | k16);
                 }
               }
-              accumulate = 1;
+              mma_commit_2cta(bar_empty(s), 3);
+              if (t == t1 - 1 && qd == TILE_M / WG_KSTAGE - 1) mma_commit_2cta(bar_acc, 3);
             }
-            mma_commit(bar_empty(s));
+            __syncwarp();
+            accumulate = 1;
             if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
           }
-        mma_commit(bar_acc);
+      }
+    } else if (lane == 0) {
+      // peer relay: this CTA's part of the stage has landed
+      for (int item = pair; item < p.num_items; item += npairs) {
+        int l, ob, t0, t1; decode(item, l, ob, t0, t1);
+        for (int i = (t1 - t0) * (TILE_M / WG_KSTAGE); i > 0; --i) {
+          mbar_wait(bar_full(s), ph);
+          mbar_arrive_remote_relaxed(mapa_shared(bar_full(s), 0));
+          if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else {
     // bias-gradient partial sums while the pipeline runs, accumulator flush at the end of each item
-    const int q = warp & 3, et = threadIdx.x - 64;      // thread <-> output feature o = ob*128 + row
+    const int q = warp & 3;                             // thread <-> output feature o = 256 ob + 128 rank + row
     const int row = q * 32 + lane;
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t accfree_addr = rank == 0 ? bar_accfree : mapa_shared(bar_accfree, 0);
     int s = 0; uint32_t ph = 0, ph_acc = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = pair; item < p.num_items; item += npairs) {
       int l, ob, t0, t1; decode(item, l, ob, t0, t1);
+      const int o = ob * 256 + (int)rank * 128 + row;
       float bsum = 0.f;
       // column `row` of the D stage: slab row>>6, element row&63 of each of the 32 point-lines
       const int bslab = row >> 6, bc8 = (row & 63) >> 3, be = row & 7;
@@ -442,14 +469,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const Wgr
           if (lane == 0) mbar_arrive(bar_empty(s));
           if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
         }
-      (void)et;
-      atomicAdd(p.gB[l] + ob * 128 + row, bsum);
-      // ---- flush dW_l[ob*128 + row, :]
+      atomicAdd(p.gB[l] + o, bsum);
+      // ---- flush dW_l[o, :]
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tcgen05_fence_after();
       const int ncols = l == 0 ? 128 : D;
       const int ld = l == 0 ? 84 : D;
-      float *wrow = p.gW[l] + (int64_t)(ob * 128 + row) * ld;
+      float *wrow = p.gW[l] + (int64_t)o * ld;
 #pragma unroll 1
       for (int g = 0; g < ncols / 32; ++g) {
         uint32_t acc[32];
@@ -467,38 +493,64 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_bf16_kernel(const Wgr
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(bar_accfree);
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(accfree_addr);
+        else mbar_arrive_remote_relaxed(accfree_addr);
+      }
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  cluster_sync_all();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc_2cta(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ output layer grads
-// gW_out[o,:] += sum_p g[p,o] h_7[p,:] ; gb_out[o] += sum_p g[p,o].  One CTA per group of tiles, thread <-> 4 columns.
-__global__ void __launch_bounds__(128) out_wgrad_bf16_kernel(const float2 *__restrict__ g, int64_t M, int num_tiles,
-                                                             int tiles_per_cta, const uint8_t *__restrict__ save_h,
-                                                             float *__restrict__ gW, float *__restrict__ gB) {
-  const int t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, num_tiles);
-  const int c0 = threadIdx.x * 4;                  // columns c0..c0+3 : slab c0>>6, chunk (c0&63)>>3, half (c0&7)>>2
-  float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, s0 = 0.f, s1 = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    const uint8_t *h7 = save_h + ((int64_t)t * NH + (NH - 1)) * A_BYTES + (c0 >> 6) * SLAB_BYTES;
-    for (int r = 0; r < TILE_M; ++r) {
-      const int64_t m = (int64_t)t * TILE_M + r;
-      if (m >= M) break;
-      const float2 gg = g[m];
-      const uint2 hv = *reinterpret_cast<const uint2 *>(h7 + sw128_chunk_off(r, (c0 & 63) >> 3) + (c0 & 7) * 2);
-      const float h[4] = {bf_lo(hv.x), bf_hi(hv.x), bf_lo(hv.y), bf_hi(hv.y)};
+// gW_out[o,:] += sum_p g[p,o] h_7[p,:] ; gb_out[o] += sum_p g[p,o].  HBM-bound stream over the saved h_7 images
+// (1 KB per point).  256 threads = 4 row groups x 64 column chunks: a warp reads 4 full 128 B image rows per
+// instruction, 8 rows (independent 16 B loads) in flight per thread; partial sums stay in registers over all the
+// tiles of the CTA, are combined across the row groups in shared memory and leave as one atomic per output.
+constexpr int OW_THREADS = 256;
+__global__ void __launch_bounds__(OW_THREADS) out_wgrad_bf16_kernel(const float2 *__restrict__ g, int64_t M, int num_tiles,
+                                                                    const uint8_t *__restrict__ save_h,
+                                                                    float *__restrict__ gW, float *__restrict__ gB) {
+  __shared__ float red[4][2 * D + 2];
+  const int rg = threadIdx.x >> 6, cg = threadIdx.x & 63;      // rows [32 rg, 32 rg + 32) ; columns [8 cg, 8 cg + 8)
+  const int slab = cg >> 3, c8 = cg & 7;
+  float a0[8], a1[8], s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { a0[j] += gg.x * h[j]; a1[j] += gg.y * h[j]; }
-      if (threadIdx.x == 0) { s0 += gg.x; s1 += gg.y; }
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint8_t *h7 = save_h + ((int64_t)t * NH + (NH - 1)) * A_BYTES + slab * SLAB_BYTES;
+#pragma unroll 1
+    for (int r0 = rg * 32; r0 < rg * 32 + 32; r0 += 8) {
+      uint4 hv[8];
+      float2 gg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        const int64_t m = (int64_t)t * TILE_M + r;
+        hv[i] = __ldcs(reinterpret_cast<const uint4 *>(h7 + sw128_chunk_off(r, c8)));
+        gg[i] = m < M ? __ldg(g + m) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float h[8] = {bf_lo(hv[i].x), bf_hi(hv[i].x), bf_lo(hv[i].y), bf_hi(hv[i].y),
+                            bf_lo(hv[i].z), bf_hi(hv[i].z), bf_lo(hv[i].w), bf_hi(hv[i].w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] = fmaf(gg[i].x, h[j], a0[j]); a1[j] = fmaf(gg[i].y, h[j], a1[j]); }
+        if (cg == 0) { s0 += gg[i].x; s1 += gg[i].y; }
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { atomicAdd(gW + c0 + j, a0[j]); atomicAdd(gW + D + c0 + j, a1[j]); }
-  if (threadIdx.x == 0) { atomicAdd(gB, s0); atomicAdd(gB + 1, s1); }
+  for (int j = 0; j < 8; ++j) { red[rg][cg * 8 + j] = a0[j]; red[rg][D + cg * 8 + j] = a1[j]; }
+  if (cg == 0) { red[rg][2 * D] = s0; red[rg][2 * D + 1] = s1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * D + 2; i += OW_THREADS) {
+    const float v = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
+    atomicAdd(i < 2 * D ? gW + i : gB + (i - 2 * D), v);
+  }
 }
 
 }  // namespace bf
@@ -556,17 +608,19 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   bf::WgradParams wp{};
   wp.save_d = w.d; wp.save_h = w.h; wp.save_enc = w.enc;
   wp.num_tiles = num_tiles;
-  int tpi = (num_tiles * 32 + 1023) / 1024;
+  // items = tile ranges x 8 layers x 2 o-blocks, about 7 per CTA pair
+  const int npairs = num_sms / 2;
+  int tpi = (num_tiles * 16 + 7 * npairs - 1) / (7 * npairs);
   if (tpi < 4) tpi = 4;
   wp.tiles_per_item = tpi;
-  wp.num_items = ((num_tiles + tpi - 1) / tpi) * 32;
+  wp.num_items = ((num_tiles + tpi - 1) / tpi) * 16;
   for (int l = 0; l < bf::NH; ++l) { wp.gW[l] = gW[l]; wp.gB[l] = gB[l]; }
-  const int wgrid = wp.num_items < num_sms ? wp.num_items : num_sms;
+  int wgrid = wp.num_items < npairs ? wp.num_items * 2 : npairs * 2;
   bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::WG_THREADS, bf::WG_SMEM_BYTES, st>>>(wp);
   if (int e = debug_sync("mlp_wgrad_bf16_kernel", st)) return e;
 
-  const int tpc = (num_tiles + 4 * num_sms - 1) / (4 * num_sms);
-  bf::out_wgrad_bf16_kernel<<<(num_tiles + tpc - 1) / tpc, 128, 0, st>>>(dp.g, M, num_tiles, tpc, w.h, gW[bf::NH], gB[bf::NH]);
+  const int ogrid = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
+  bf::out_wgrad_bf16_kernel<<<ogrid, bf::OW_THREADS, 0, st>>>(dp.g, M, num_tiles, w.h, gW[bf::NH], gB[bf::NH]);
   count_launch(3);
   return launch_status();
 }
