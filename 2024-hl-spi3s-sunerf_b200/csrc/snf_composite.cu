@@ -13,102 +13,134 @@ namespace snf {
 constexpr int kRayWarps = 4;  // warps (= rays) per CTA for the per-ray kernels
 
 // ------------------------------------------------------------------------------------------------ K5
+// One warp per ray, lane <-> sample c*32 + lane of chunk c.  Every global load of the ray is issued before the first
+// use (S = 192: 2.3 KB in flight per warp), the whole ray lives in registers, neighbours come from shuffles; the
+// only serial dependence is the carry of the exclusive product between the NCH chunk scans.
+// dz of a sample: z[j] - z[j-1], the first one z[1] - z[0] (emission.py:24-29).
+template <int NCH>
+__device__ __forceinline__ void ray_dz(const float (&zr)[NCH], int lane, float dnorm, int S, float (&dz)[NCH]) {
+  const float z1 = __shfl_sync(kFull, zr[0], 1);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float up = __shfl_up_sync(kFull, zr[c], 1);
+    const float prev31 = __shfl_sync(kFull, zr[c > 0 ? c - 1 : 0], 31);
+    const float d = lane > 0 ? fsub(zr[c], up) : (c > 0 ? fsub(zr[c], prev31) : fsub(z1, zr[0]));
+    dz[c] = fmul(d, dnorm);
+  }
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(kRayWarps * 32)
     composite_emission_fwd_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
                                   const float *__restrict__ rays_d, int64_t N, int S, float *__restrict__ image,
                                   float *__restrict__ weights, float *__restrict__ absorption) {
-  extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
   if (ray >= N) return;
-  float *zs = sm + (size_t)warp * 2 * S, *Ps = zs + S;
-  for (int j = lane; j < S; j += 32) zs[j] = z[ray * S + j];
+  float zr[NCH];
+  float2 rw[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = c * 32 + lane;
+    zr[c] = j < S ? __ldcs(z + ray * S + j) : 0.f;
+    rw[c] = j < S ? __ldcs(raw + ray * S + j) : make_float2(0.f, 0.f);
+  }
   const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
   const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));      // :29
-  __syncwarp();
+  float dz[NCH], P[NCH];
+  ray_dz<NCH>(zr, lane, dnorm, S, dz);
   double carry = 1.0, isum = 0.0;
-  for (int base = 0; base < S; base += 32) {
-    const int j = base + lane;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = c * 32 + lane;
     const bool ok = j < S;
-    float P = 0.f, f = 1.f;
+    float E = 0.f, f = 1.f;
     if (ok) {
-      const float dz = fmul(j == 0 ? fsub(zs[1], zs[0]) : fsub(zs[j], zs[j - 1]), dnorm);   // :24-29
-      const float2 r = raw[ray * S + j];
-      const float E = fmul(expf(r.x), dz);                                                   // :34
-      const float a = expf(fmul(-fmaxf(r.y, 0.f), dz));                                      // :37
-      absorption[ray * S + j] = a;
-      f = fadd(a, 1e-10f);                                                                   // :43
-      P = E;
+      E = fmul(expf(rw[c].x), dz[c]);                                                    // :34
+      const float a = expf(fmul(-fmaxf(rw[c].y, 0.f), dz[c]));                           // :37
+      __stcs(absorption + ray * S + j, a);
+      f = fadd(a, 1e-10f);                                                               // :43
     }
     const double incl = warp_incl_prod((double)f, lane);
     double excl = shfl_up_d(incl, 1);
     if (lane == 0) excl = 1.0;
     const float T = (float)(carry * excl);     // exclusive cumprod, double accumulate -> float per prefix
-    P = fmul(P, T);                                                                           // :46
-    if (ok) { Ps[j] = P; isum += (double)P; }
+    P[c] = fmul(E, T);                                                                   // :46
+    isum += (double)P[c];
     carry *= __shfl_sync(kFull, incl, 31);
   }
-  const float I = (float)warp_sum(isum);                                                      // :48
+  const float I = (float)warp_sum(isum);                                                 // :48
   if (lane == 0) image[ray] = I;
   const float den = fadd(I, 1e-10f);
-  __syncwarp();
-  for (int j = lane; j < S; j += 32) weights[ray * S + j] = fdiv(Ps[j], den);                 // :51-52
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = c * 32 + lane;
+    if (j < S) __stcs(weights + ray * S + j, fdiv(P[c], den));                           // :51-52
+  }
 }
 
 // dI/draw0[k] = P_k ; dI/draw1[j] = -1[raw1>0] dz_j a_j (sum_{k>j} P_k)/(a_j+1e-10) ; plus dL/da from g_absorption
+template <int NCH>
 __global__ void __launch_bounds__(kRayWarps * 32)
     composite_emission_bwd_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
                                   const float *__restrict__ rays_d, int64_t N, int S,
                                   const float *__restrict__ g_image, const float *__restrict__ g_abs,
                                   float2 *__restrict__ g_raw) {
-  extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
   if (ray >= N) return;
-  float *zs = sm + (size_t)warp * 4 * S, *Ps = zs + S, *As = Ps + S, *Dz = As + S;
-  for (int j = lane; j < S; j += 32) zs[j] = z[ray * S + j];
+  float zr[NCH], ga_in[NCH];
+  float2 rw[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = c * 32 + lane;
+    zr[c] = j < S ? __ldcs(z + ray * S + j) : 0.f;
+    rw[c] = j < S ? __ldcs(raw + ray * S + j) : make_float2(0.f, 0.f);
+    ga_in[c] = (g_abs != nullptr && j < S) ? __ldcs(g_abs + ray * S + j) : 0.f;
+  }
   const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
   const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));
   const float g = g_image[ray];
-  __syncwarp();
+  float dz[NCH], P[NCH], A[NCH];
+  ray_dz<NCH>(zr, lane, dnorm, S, dz);
   double carry = 1.0;
-  for (int base = 0; base < S; base += 32) {
-    const int j = base + lane;
-    const bool ok = j < S;
-    float E = 0.f, f = 1.f, a = 1.f, dz = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const bool ok = c * 32 + lane < S;
+    float E = 0.f, f = 1.f, a = 1.f;
     if (ok) {
-      dz = fmul(j == 0 ? fsub(zs[1], zs[0]) : fsub(zs[j], zs[j - 1]), dnorm);
-      const float2 r = raw[ray * S + j];
-      E = fmul(expf(r.x), dz);
-      a = expf(fmul(-fmaxf(r.y, 0.f), dz));
+      E = fmul(expf(rw[c].x), dz[c]);
+      a = expf(fmul(-fmaxf(rw[c].y, 0.f), dz[c]));
       f = fadd(a, 1e-10f);
     }
     const double incl = warp_incl_prod((double)f, lane);
     double excl = shfl_up_d(incl, 1);
     if (lane == 0) excl = 1.0;
     const float T = (float)(carry * excl);
-    if (ok) { Ps[j] = fmul(E, T); As[j] = a; Dz[j] = dz; }
+    P[c] = ok ? fmul(E, T) : 0.f;
+    A[c] = a;
     carry *= __shfl_sync(kFull, incl, 31);
   }
-  __syncwarp();
-  // reverse pass: exclusive suffix sums of P
-  double rcarry = 0.0;
-  const int nchunk = (S + 31) / 32;
-  for (int c = nchunk - 1; c >= 0; --c) {
+  // reverse pass: exclusive suffix sums of P (fp32 is ample for the 1e-3 gradient tolerance: autograd itself is fp32)
+  float rcarry = 0.f;
+#pragma unroll
+  for (int c = NCH - 1; c >= 0; --c) {
     const int j = c * 32 + lane;
-    const bool ok = j < S;
-    const double p = ok ? (double)Ps[j] : 0.0;
-    const double suf = warp_suffix_sum(p, lane) + rcarry;   // inclusive
-    const double suf_excl = suf - p;
-    if (ok) {
-      const float2 r = raw[ray * S + j];
-      const float a = As[j];
-      float ga = (float)((double)g * suf_excl / (double)fadd(a, 1e-10f));
-      if (g_abs != nullptr) ga += g_abs[ray * S + j];
+    float suf = P[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float n = __shfl_down_sync(kFull, suf, d);
+      if (lane + d < 32) suf += n;
+    }
+    suf += rcarry;                                          // inclusive
+    const float suf_excl = suf - P[c];
+    if (j < S) {
+      const float a = A[c];
+      const float ga = g * suf_excl / fadd(a, 1e-10f) + ga_in[c];
       float2 o;
-      o.x = g * Ps[j];
-      o.y = (r.y > 0.f) ? -ga * Dz[j] * a : 0.f;
-      g_raw[ray * S + j] = o;
+      o.x = g * P[c];
+      o.y = (rw[c].y > 0.f) ? -ga * dz[c] * a : 0.f;
+      __stcs(g_raw + ray * S + j, o);
     }
     rcarry = __shfl_sync(kFull, suf, 0);
   }
@@ -449,9 +481,15 @@ extern "C" int snf_composite_emission_fwd(const float *raw, const float *z, cons
   if (N < 0 || S < 2) return SNF_E_ARG;
   if (S > 256) return SNF_E_SHAPE;
   if (N == 0) return 0;
-  composite_emission_fwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32,
-                                  (size_t)kRayWarps * 2 * S * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2 *>(raw), z, rays_d, N, S, image, weights, absorption);
+  const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
+  const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
+#define SNF_LAUNCH(NCH) \
+  composite_emission_fwd_kernel<NCH><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, S, image, weights, absorption)
+  switch ((S + 31) / 32) {
+    case 1: SNF_LAUNCH(1); break; case 2: SNF_LAUNCH(2); break; case 3: SNF_LAUNCH(3); break; case 4: SNF_LAUNCH(4); break;
+    case 5: SNF_LAUNCH(5); break; case 6: SNF_LAUNCH(6); break; case 7: SNF_LAUNCH(7); break; default: SNF_LAUNCH(8); break;
+  }
+#undef SNF_LAUNCH
   count_launch();
   return launch_status();
 }
@@ -464,10 +502,16 @@ extern "C" int snf_composite_emission_bwd(const float *raw, const float *z, cons
   if (N < 0 || S < 2) return SNF_E_ARG;
   if (S > 256) return SNF_E_SHAPE;
   if (N == 0) return 0;
-  composite_emission_bwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32,
-                                  (size_t)kRayWarps * 4 * S * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2 *>(raw), z, rays_d, N, S, g_image, g_absorption,
-      reinterpret_cast<float2 *>(g_raw));
+  const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
+  const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
+  float2 *g2 = reinterpret_cast<float2 *>(g_raw);
+#define SNF_LAUNCH(NCH) \
+  composite_emission_bwd_kernel<NCH><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, S, g_image, g_absorption, g2)
+  switch ((S + 31) / 32) {
+    case 1: SNF_LAUNCH(1); break; case 2: SNF_LAUNCH(2); break; case 3: SNF_LAUNCH(3); break; case 4: SNF_LAUNCH(4); break;
+    case 5: SNF_LAUNCH(5); break; case 6: SNF_LAUNCH(6); break; case 7: SNF_LAUNCH(7); break; default: SNF_LAUNCH(8); break;
+  }
+#undef SNF_LAUNCH
   count_launch();
   return launch_status();
 }

@@ -9,20 +9,21 @@ namespace snf {
 unsigned long long g_launches = 0;
 
 // ------------------------------------------------------------------------------------------------
-// K1: one thread per (ray, sample).  The per-ray scalars (shell entry/exit) are recomputed by every
-// thread of the ray: ~25 flops against 12 B of traffic per element, and it keeps every access of the
-// [N,S] streams perfectly coalesced.
+// K1: one warp per 32 rays.  Lane r computes the shell entry/exit of ray r once (two square roots and a
+// division), then the warp walks over its rays: the scalars are broadcast by shuffle and lane <-> sample,
+// so every access of the [N,S] streams is a full coalesced row and no per-ray work is repeated per sample.
 // ------------------------------------------------------------------------------------------------
+template <int NJ>
 __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict__ rays_o,
                                                          const float *__restrict__ rays_d,
                                                          const float *__restrict__ t_vals,
                                                          const float *__restrict__ t_rand, int64_t N, int S,
                                                          float D, float solar_R, float *__restrict__ z_out,
-                                                         float *__restrict__ pts_out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * S) return;
-  const int64_t i = idx / S;
-  const int j = (int)(idx - i * S);
+                                                         float *__restrict__ pts_out, int rpw /* rays per warp, <= 32 */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw;
+  if (ray0 >= N) return;
+  const int64_t i = (lane < rpw && ray0 + lane < N) ? ray0 + lane : ray0;
   const float o0 = rays_o[3 * i], o1 = rays_o[3 * i + 1], o2 = rays_o[3 * i + 2];
   const float d0 = rays_d[3 * i], d1 = rays_d[3 * i + 1], d2 = rays_d[3 * i + 2];
   const float osq = sum3(fmul(o0, o0), fmul(o1, o1), fmul(o2, o2));
@@ -32,24 +33,43 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
   const float qc = fsub(osq, fmul(solar_R, solar_R));                             // :80
   const float disc = fsub(fmul(qb, qb), fmul(fmul(4.f, qa), qc));
   const float hit = fdiv(fsub(-qb, __fsqrt_rn(disc)), fmul(2.f, qa));             // :81 (NaN on a miss)
-  const float z_near = fsub(r_obs, D);                                            // :83
-  float z_far = fadd(r_obs, D);                                                   // :84
-  if (hit == hit) z_far = hit;                                                    // :87-88
-  auto bin_edge = [&](int k) {                                                    // :90
-    const float t = t_vals[k];
-    return fadd(fmul(z_near, fsub(1.f, t)), fmul(z_far, t));
-  };
-  float z = bin_edge(j);
-  if (t_rand != nullptr) {                                                        // :93-98
-    const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
-    const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
-    z = fadd(lo, fmul(fsub(hi, lo), t_rand[idx]));
-  }
-  z_out[idx] = z;
-  if (pts_out != nullptr) {                                                       // :100
-    pts_out[3 * idx] = fadd(o0, fmul(d0, z));
-    pts_out[3 * idx + 1] = fadd(o1, fmul(d1, z));
-    pts_out[3 * idx + 2] = fadd(o2, fmul(d2, z));
+  const float my_near = fsub(r_obs, D);                                           // :83
+  float my_far = fadd(r_obs, D);                                                  // :84
+  if (hit == hit) my_far = hit;                                                   // :87-88
+  const int nr = (int)(N - ray0 < rpw ? N - ray0 : rpw);
+#pragma unroll 4
+  for (int r = 0; r < nr; ++r) {
+    const float z_near = __shfl_sync(kFull, my_near, r), z_far = __shfl_sync(kFull, my_far, r);
+    const float p0 = __shfl_sync(kFull, o0, r), p1 = __shfl_sync(kFull, o1, r), p2 = __shfl_sync(kFull, o2, r);
+    const float e0 = __shfl_sync(kFull, d0, r), e1 = __shfl_sync(kFull, d1, r), e2 = __shfl_sync(kFull, d2, r);
+    auto bin_edge = [&](int k) {                                                  // :90
+      const float t = __ldg(t_vals + k);
+      return fadd(fmul(z_near, fsub(1.f, t)), fmul(z_far, t));
+    };
+    auto sample = [&](int j, float tr, int64_t row) {
+      float z = bin_edge(j);
+      if (t_rand != nullptr) {                                                    // :93-98
+        const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
+        const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
+        z = fadd(lo, fmul(fsub(hi, lo), tr));
+      }
+      __stcs(z_out + row + j, z);
+      if (pts_out != nullptr) {                                                   // :100
+        pts_out[3 * (row + j)] = fadd(p0, fmul(e0, z));
+        pts_out[3 * (row + j) + 1] = fadd(p1, fmul(e1, z));
+        pts_out[3 * (row + j) + 2] = fadd(p2, fmul(e2, z));
+      }
+    };
+    const int64_t row = (ray0 + r) * S;
+    if (NJ > 0) {   // S == 32 NJ: every load of the row is issued before the first use
+      float tr[NJ > 0 ? NJ : 1];
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) tr[k] = t_rand != nullptr ? __ldcs(t_rand + row + k * 32 + lane) : 0.f;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) sample(k * 32 + lane, tr[k], row);
+    } else {
+      for (int j = lane; j < S; j += 32) sample(j, t_rand != nullptr ? __ldcs(t_rand + row + j) : 0.f, row);
+    }
   }
 }
 
@@ -199,9 +219,13 @@ extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, c
   SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(t_vals); SNF_CHECK_PTR(z_vals);
   if (N < 0 || S <= 0) return SNF_E_ARG;
   if (N == 0) return 0;
-  const int64_t total = N * S;
-  stratified_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points);
+  int rpw = 32;                                   // small batches: fewer rays per warp so the grid still fills the GPU
+  while (rpw > 1 && N / rpw < 148 * 16) rpw >>= 1;
+  const unsigned grid = (unsigned)ceil_div64(N, 8 * rpw);
+  if (S == 64)
+    stratified_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw);
+  else
+    stratified_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw);
   count_launch();
   return launch_status();
 }
