@@ -13,6 +13,8 @@ constexpr int NH = 8;                        // hidden layers
 constexpr int K0 = 96;                       // layer-0 K: 84 features + 4 bf16 residuals of x + 8 zero columns
 constexpr int SLAB_BYTES = TILE_M * 128;     // one K-slab (64 bf16) of a 128-row image: 16 KB
 constexpr int A_BYTES = 8 * SLAB_BYTES;      // 128 KB activation image
+constexpr int C_BYTES = TILE_M * D;          // 64 KB: cos(pre) of one tile and layer as int8 (x 127), chunk-major:
+                                             // [slab (8)][ch (2)][k (2)][row (128)] x 16 B; a warp access covers 512 B
 
 // ---- layer-chain kernels (forward, dgrad): CTA pairs, tcgen05 cta_group::2, M=256 N=256 K=16
 constexpr int NCHUNK = 256;                  // output features per MMA / per weight block
@@ -52,6 +54,21 @@ constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYT
 
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// cos(pre) travels from the forward to the dgrad chain as int8 = rint(127 cos): absolute error <= 1/254, about what
+// a bf16 pre-activation gave for |pre| ~ 2, at half the HBM bytes (the forward is bound by HBM writes).
+// Encode: 127 c + 1.5 * 2^23 leaves the two's-complement integer in the low mantissa byte.
+__device__ __forceinline__ uint32_t cosq_pack4(float c0, float c1, float c2, float c3) {
+  const uint32_t t0 = __float_as_uint(fmaf(c0, 127.f, 12582912.f)), t1 = __float_as_uint(fmaf(c1, 127.f, 12582912.f));
+  const uint32_t t2 = __float_as_uint(fmaf(c2, 127.f, 12582912.f)), t3 = __float_as_uint(fmaf(c3, 127.f, 12582912.f));
+  return __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
+}
+// Decode byte b of w ^ 0x80808080 (offset binary): 2^23 + u as float bits; the subtraction is exact, so the only
+// rounding is the final scaling.
+__device__ __forceinline__ float cosq_get(uint32_t wx, int b) {
+  const uint32_t f = __byte_perm(wx, 0x4B000000u, 0x7650 + b);   // bytes: [wx.b, 0x00, 0x00, 0x4B]
+  return (__uint_as_float(f) - 8388736.f) * (1.f / 127.f);
+}
 
 // Barrier block (8 bytes each) inside [OFF_BAR, OFF_BAR + 256)
 //   full[s]   : this CTA's half of stage s has landed (TMA complete_tx); on the LEADER it additionally counts one
@@ -95,7 +112,8 @@ struct Bars {
 constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
 }  // namespace fw
 
-// saved-image workspace (training): [enc][H = sin(pre)][P = pre][D = dL/dpre], all [tile][layer][128 KB] bf16 images.
+// saved-image workspace (training): [enc][H = sin(pre)][D = dL/dpre] as [tile][layer][128 KB] bf16 images and
+// [C = cos(pre)] as [tile][layer][64 KB] int8.
 // Sized for an even number of tiles (CTA pairs always process two).
 struct Bf16Ws {
   uint8_t *enc, *h, *pre, *d;
@@ -110,7 +128,7 @@ inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
   if (train) {
     w.enc = p + off; off += tiles * 2 * SLAB_BYTES;
     w.h = p + off; off += tiles * NH * (int64_t)A_BYTES;
-    w.pre = p + off; off += tiles * NH * (int64_t)A_BYTES;
+    w.pre = p + off; off += tiles * NH * (int64_t)C_BYTES;   // quantised cos(pre), see C_BYTES
     w.d = p + off; off += tiles * NH * (int64_t)A_BYTES;
   }
   w.bytes = off > 0 ? off : 256;

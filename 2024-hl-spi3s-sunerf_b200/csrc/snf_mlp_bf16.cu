@@ -13,7 +13,7 @@
 //                              for the next layer; layer 0's A image is the sin/cos encoding computed in place;
 //                              the 512->2 output layer is a register dot product fused into the last epilogue
 // Training mode additionally writes, per layer, the activation image h = sin(pre) (TMA bulk store straight from the
-// A image) and the pre-activation image (bf16, direct 16 B stores) in the same tile-image layout for the backward.
+// A image) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
 #include "snf_bf16_common.cuh"
 
 namespace snf {
@@ -82,7 +82,7 @@ struct FwdParams {
   float off0, off1;
   uint8_t *save_enc;      // train: [tiles][2 slabs][16 KB] bf16 image, else null
   uint8_t *save_h;        // train: [tiles][8][128 KB]   sin(pre)
-  uint8_t *save_pre;      // train: [tiles][8][128 KB]   pre-activation (the backward takes cos of it)
+  uint8_t *save_pre;      // train: [tiles][8][64 KB]    cos(pre) as int8 (C_BYTES layout) for the dgrad chain
 };
 
 #ifdef SNF_PROF
@@ -319,7 +319,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         const bool last = (l == NH - 1);
         const float *bl = bias_s + (l & 1) * D;
         uint8_t *hsave = TRAIN ? p.save_h + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
-        uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
+        uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * C_BYTES : nullptr;
         uint32_t held[64];                            // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
@@ -370,7 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
             if (j + 1 < 4) tmem_ld32(tm_row + h * 256 + (j + 1) * 64, nxt);
             const int col0 = h * 256 + j * 64 + ch * 32;
             const int sl = h * 4 + j;
-            uint32_t pk[16], ppk[16];
+            uint32_t pk[16], cq[8];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 b = *reinterpret_cast<const float4 *>(bl + col0 + i);
@@ -382,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
 #endif
               pk[i / 2] = pack_bf16x2(s0, s1); pk[i / 2 + 1] = pack_bf16x2(s2, s3);
-              if (TRAIN) { ppk[i / 2] = pack_bf16x2(v0, v1); ppk[i / 2 + 1] = pack_bf16x2(v2, v3); }
+              if (TRAIN) cq[i / 4] = cosq_pack4(__cosf(v0), __cosf(v1), __cosf(v2), __cosf(v3));
               if (last) {   // fused output layer: out = W_out h + b_out
                 const float4 wa = *reinterpret_cast<const float4 *>(wout_s + col0 + i);
                 const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + col0 + i);
@@ -390,10 +390,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 o1 += s0 * wb.x + s1 * wb.y + s2 * wb.z + s3 * wb.w;
               }
             }
-            if (TRAIN) {   // pre-activation, chunk-major layout [slab][chunk][row] x 16 B: a warp store covers 512 contiguous bytes
+            if (TRAIN) {   // cos(pre) for the dgrad chain: 2 x 16 B per thread, a warp store covers 512 contiguous bytes
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                st_stream16(psave + (((sl * 8 + 4 * ch + c) * TILE_M + row) << 4), ppk[4 * c], ppk[4 * c + 1], ppk[4 * c + 2], ppk[4 * c + 3]);
+              for (int k = 0; k < 2; ++k)
+                st_stream16(psave + ((((sl * 2 + ch) * 2 + k) * TILE_M + row) << 4), cq[4 * k], cq[4 * k + 1], cq[4 * k + 2], cq[4 * k + 3]);
             }
             if (!last || TRAIN) {
               if (h == 0) {

@@ -47,7 +47,7 @@ struct DgradParams {
   int64_t M;
   int num_tiles;            // even
   const uint8_t *packed;    // forward pack + W^T blocks
-  const uint8_t *save_pre;  // [tiles][8][128 KB] pre-activations, chunk-major layout (snf_mlp_bf16.cu)
+  const uint8_t *save_pre;  // [tiles][8][64 KB] cos(pre) as int8, C_BYTES layout (written by the forward)
   uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
@@ -57,6 +57,7 @@ __device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+// dpre_{l-1} = (dpre_l W_l) * cos(pre_{l-1}); the cosines come from the forward as int8 (C_BYTES images).
 // Same overlapped structure as the forward (snf_mlp_bf16.cu): per layer two temporal N-halves, the epilogue of half 0
 // runs under the MMAs of half 1 and keeps its result in registers until the A image may be overwritten; the next
 // layer's MMAs start slab by slab.  Shared-memory layout and barriers: namespace fw (the bias area is unused).
@@ -93,13 +94,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     // pre-activation images about one layer ahead of the epilogue that multiplies by their cosine
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      auto pre_img = [&](int tile, int l) { return p.save_pre + ((int64_t)tile * NH + l) * A_BYTES; };
+      auto pre_img = [&](int tile, int l) { return p.save_pre + ((int64_t)tile * NH + l) * C_BYTES; };
       {
         const int tile = pair * 2 + (int)rank;
         if (tile < p.num_tiles)
           for (int sl = 0; sl < 8; ++sl) {
-            prefetch_l2(pre_img(tile, NH - 1) + sl * SLAB_BYTES, SLAB_BYTES);
-            prefetch_l2(pre_img(tile, NH - 2) + sl * SLAB_BYTES, SLAB_BYTES);
+            prefetch_l2(pre_img(tile, NH - 1) + sl * (C_BYTES / 8), C_BYTES / 8);
+            prefetch_l2(pre_img(tile, NH - 2) + sl * (C_BYTES / 8), C_BYTES / 8);
           }
       }
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
@@ -110,9 +111,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
             bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
             if (l >= 2) {
-              if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * SLAB_BYTES, SLAB_BYTES);
+              if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * (C_BYTES / 8), C_BYTES / 8);
             } else if (next_tile < p.num_tiles) {   // l == 1: the next tile's first two images
-              prefetch_l2(pre_img(next_tile, b < 8 ? NH - 1 : NH - 2) + (b & 7) * SLAB_BYTES, SLAB_BYTES);
+              prefetch_l2(pre_img(next_tile, b < 8 ? NH - 1 : NH - 2) + (b & 7) * (C_BYTES / 8), C_BYTES / 8);
             }
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
@@ -174,11 +175,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // this thread's 32 pre-activations of one step: 4 chunks of 8 bf16 in the chunk-major layout
-    auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[4]) {
+    // this thread's 32 cosines of one step: 2 x 16 int8, offset-binary after the XOR (cosq_get)
+    auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[2]) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        pv[c] = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 8 + 4 * ch + c) * TILE_M + row) << 4)));
+      for (int k = 0; k < 2; ++k) {
+        uint4 v = __ldcs(reinterpret_cast<const uint4 *>(img + ((((sl * 2 + ch) * 2 + k) * TILE_M + row) << 4)));
+        v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+        pv[k] = v;
+      }
+    };
+    auto cos_of = [&](const uint4 (&pv)[2], int i) {   // element i (0..31) of the step
+      const uint4 &v = pv[i >> 4];
+      const int wi = (i >> 2) & 3;
+      const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
+      return cosq_get(w, i & 3);
     };
     // slab sl of the A image is complete for this pair's 32 rows: hand it to the MMAs and store it for the wgrad
     auto publish = [&](uint8_t *dimg, int sl0, int nsl) {
@@ -194,12 +204,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
       const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
-      const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * A_BYTES;
+      const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * C_BYTES;
       uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
-      uint4 pn[4];
+      uint4 pn[2];
       // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7), written straight into the A image
       {
-        const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * A_BYTES;
+        const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * C_BYTES;
         uint8_t *d7 = d_tile + (int64_t)(NH - 1) * A_BYTES;
         load_pre(p7, 0, pn);
         float2 gg = make_float2(0.f, 0.f);
@@ -208,21 +218,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         named_bar_sync(2 + q, 64);
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
-          uint4 pv[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) pv[c] = pn[c];
+          uint4 pv[2];
+          pv[0] = pn[0]; pv[1] = pn[1];
           if (sl + 1 < 8) load_pre(p7, sl + 1, pn);
-          else load_pre(pre_tile + (int64_t)(NH - 2) * A_BYTES, 0, pn);
+          else load_pre(pre_tile + (int64_t)(NH - 2) * C_BYTES, 0, pn);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int col = sl * 64 + (4 * ch + c) * 8;
             const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col), wa1 = *reinterpret_cast<const float4 *>(wout_s + col + 4);
             const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col + 4);
             uint4 o;
-            o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * __cosf(bf_lo(pv[c].x)), (gg.x * wa0.y + gg.y * wb0.y) * __cosf(bf_hi(pv[c].x)));
-            o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * __cosf(bf_lo(pv[c].y)), (gg.x * wa0.w + gg.y * wb0.w) * __cosf(bf_hi(pv[c].y)));
-            o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * __cosf(bf_lo(pv[c].z)), (gg.x * wa1.y + gg.y * wb1.y) * __cosf(bf_hi(pv[c].z)));
-            o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * __cosf(bf_lo(pv[c].w)), (gg.x * wa1.w + gg.y * wb1.w) * __cosf(bf_hi(pv[c].w)));
+            o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * cos_of(pv, 8 * c + 0), (gg.x * wa0.y + gg.y * wb0.y) * cos_of(pv, 8 * c + 1));
+            o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * cos_of(pv, 8 * c + 2), (gg.x * wa0.w + gg.y * wb0.w) * cos_of(pv, 8 * c + 3));
+            o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * cos_of(pv, 8 * c + 4), (gg.x * wa1.y + gg.y * wb1.y) * cos_of(pv, 8 * c + 5));
+            o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * cos_of(pv, 8 * c + 6), (gg.x * wa1.w + gg.y * wb1.w) * cos_of(pv, 8 * c + 7));
             *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) = o;
           }
           publish(d7, sl, 1);
@@ -235,8 +244,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       for (int l = NH - 1; l >= 1; --l) {
         // accumulator = dpre_l W_l = dL/dh_{l-1}; multiply by cos(pre_{l-1}) -> dpre_{l-1}
         const bool last = (l == 1);
-        const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * A_BYTES;
-        const uint8_t *pnext = pre_tile + (int64_t)(l >= 2 ? l - 2 : 0) * A_BYTES;
+        const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * C_BYTES;
+        const uint8_t *pnext = pre_tile + (int64_t)(l >= 2 ? l - 2 : 0) * C_BYTES;
         uint8_t *dprev = d_tile + (int64_t)(l - 1) * A_BYTES;
         uint32_t held[64];
 #pragma unroll
@@ -261,21 +270,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int sl = h * 4 + j;
-            uint4 pv[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pv[c] = pn[c];
+            uint4 pv[2];
+            pv[0] = pn[0]; pv[1] = pn[1];
             if (sl + 1 < 8) load_pre(pprev, sl + 1, pn);
             else if (!last) load_pre(pnext, 0, pn);
             uint32_t pk[16];
             auto half_step = [&](const uint32_t (&a)[16], int c0) {   // 16 columns = chunks c0, c0 + 1 of this step
 #pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                const uint4 pw = pv[c0 + c];
-                pk[4 * (c0 + c) + 0] = pack_bf16x2(__uint_as_float(a[c * 8 + 0]) * __cosf(bf_lo(pw.x)), __uint_as_float(a[c * 8 + 1]) * __cosf(bf_hi(pw.x)));
-                pk[4 * (c0 + c) + 1] = pack_bf16x2(__uint_as_float(a[c * 8 + 2]) * __cosf(bf_lo(pw.y)), __uint_as_float(a[c * 8 + 3]) * __cosf(bf_hi(pw.y)));
-                pk[4 * (c0 + c) + 2] = pack_bf16x2(__uint_as_float(a[c * 8 + 4]) * __cosf(bf_lo(pw.z)), __uint_as_float(a[c * 8 + 5]) * __cosf(bf_hi(pw.z)));
-                pk[4 * (c0 + c) + 3] = pack_bf16x2(__uint_as_float(a[c * 8 + 6]) * __cosf(bf_lo(pw.w)), __uint_as_float(a[c * 8 + 7]) * __cosf(bf_hi(pw.w)));
-              }
+              for (int i = 0; i < 16; i += 2)
+                pk[4 * c0 + i / 2] = pack_bf16x2(__uint_as_float(a[i]) * cos_of(pv, 8 * c0 + i),
+                                                 __uint_as_float(a[i + 1]) * cos_of(pv, 8 * c0 + i + 1));
             };
             tmem_ld_wait(accA);
             tmem_ld16(tm_row + h * 256 + j * 64 + 16, accB);
