@@ -58,10 +58,12 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // cos(pre) travels from the forward to the dgrad chain as int8 = rint(127 cos): absolute error <= 1/254, about what
 // a bf16 pre-activation gave for |pre| ~ 2, at half the HBM bytes (the forward is bound by HBM writes).
 // Encode: 127 c + 1.5 * 2^23 leaves the two's-complement integer in the low mantissa byte.
-__device__ __forceinline__ uint32_t cosq_pack4(float c0, float c1, float c2, float c3) {
-  const uint32_t t0 = __float_as_uint(fmaf(c0, 127.f, 12582912.f)), t1 = __float_as_uint(fmaf(c1, 127.f, 12582912.f));
-  const uint32_t t2 = __float_as_uint(fmaf(c2, 127.f, 12582912.f)), t3 = __float_as_uint(fmaf(c3, 127.f, 12582912.f));
-  return __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
+constexpr float COSQ_MAGIC = 12582912.f;
+__device__ __forceinline__ float cosq_enc(float v) { return fmaf(__cosf(v), 127.f, COSQ_MAGIC); }
+// (An FMA-pipe polynomial for half of the cosines was measured: no gain, the training epilogue is then issue-bound.)
+__device__ __forceinline__ uint32_t cosq_pack4(float t0, float t1, float t2, float t3) {   // four encoded values -> 4 int8
+  return __byte_perm(__byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0040),
+                     __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0040), 0x5410);
 }
 // Decode byte b of w ^ 0x80808080 (offset binary): 2^23 + u as float bits; the subtraction is exact, so the only
 // rounding is the final scaling.

@@ -85,6 +85,9 @@ struct FwdParams {
   uint8_t *save_pre;      // train: [tiles][8][64 KB]    cos(pre) as int8 (C_BYTES layout) for the dgrad chain
 };
 
+#ifndef SNF_TRACE_TRAIN
+#define SNF_TRACE_TRAIN 0
+#endif
 #ifdef SNF_PROF
 __device__ unsigned long long g_prof[2][148 * 8];
 __device__ long long g_trace[4][512];   // CTA 0, inference: clock stamps per ring block
@@ -141,14 +144,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     // =========================== TMA producer (each CTA streams its half of every weight block)
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      const uint64_t keep = l2_policy_evict_last();
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
         for (int blk = 0; blk < FWD_BLOCKS; ++blk) {
           mbar_wait(bar.empty(s), ph ^ 1);
 #ifdef SNF_PROF
-          if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && blk < 512) g_trace[0][blk] = clock64();
+          if (TRAIN == SNF_TRACE_TRAIN && blockIdx.x == 0 && tp == pair + npairs && blk < 512) g_trace[0][blk] = clock64();
 #endif
           mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
-          bulk_g2s(sW + s * WHALF_BYTES, p.packed + (int64_t)blk * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
+          bulk_g2s_hint(sW + s * WHALF_BYTES, p.packed + (int64_t)blk * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s), keep);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
@@ -181,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 else if (ks >= 4) wait_ready(ks - 3);     // slab ks (ks == 7: D half 1 drained as well)
               }
 #ifdef SNF_PROF
-              if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[1][tblk] = clock64();
+              if (TRAIN == SNF_TRACE_TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[1][tblk] = clock64();
 #endif
               {
                 PROF_T0(t0);
@@ -189,7 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 PROF_ADD(t_full, t0);
               }
 #ifdef SNF_PROF
-              if (!TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[2][tblk] = clock64();
+              if (TRAIN == SNF_TRACE_TRAIN && blockIdx.x == 0 && tp == pair + npairs && lane == 0) g_trace[2][tblk] = clock64();
               ++tblk;
 #endif
               tcgen05_fence_after();
@@ -245,8 +249,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
 #pragma unroll
     for (int k = 0; k < 5; ++k) ready_addr[k] = rank == 0 ? bar.ready(k) : mapa_shared(bar.ready(k), 0);
     // one arrival per warp: every lane has fenced its own writes, __syncwarp orders them before lane 0's release
+#ifdef SNF_PROF
+    int estamp = 0; bool etrace = false;
+#define ESTAMP() do { if (etrace && e == 0 && lane == 0 && estamp < 512) g_trace[3][estamp++] = clock64(); } while (0)
+#else
+#define ESTAMP()
+#endif
     auto arrive_ready = [&](int k) {
       __syncwarp();
+      ESTAMP();
       if (lane == 0) {
         // the writes were handed to the async proxy by each lane's fence.proxy.async; the arrival itself is a signal
         if (rank == 0) mbar_arrive(ready_addr[k]);
@@ -254,12 +265,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
       }
     };
     uint32_t ph = 0;
+    const uint64_t stream_pol = l2_policy_evict_first();   // saved activations: written once, read by the backward much later
     PROF_DECL(t_acc0); PROF_DECL(t_acc1); PROF_DECL(t_enc); PROF_T0(t_begin);
     tcgen05_fence_before();
     arrive_ready(4);                                  // D half 1 is free for the first tile
     for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
       const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
+#ifdef SNF_PROF
+      etrace = TRAIN == SNF_TRACE_TRAIN && blockIdx.x == 0 && tp == pair + npairs;
+#endif
       // ---- layer-0 operand: positional encoding of this row, written straight into the A image (slabs 0, 1).
       //      ch 0: x and frequencies 0..4 ; ch 1: bf16 residual of x, zero padding and frequencies 5..9
       {
@@ -303,8 +318,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
           named_bar_sync(2 + q, 64);
           if (ch == 0 && lane == 0) {
             uint8_t *esave = p.save_enc + (int64_t)tile * 2 * SLAB_BYTES + q * PAIR_BYTES;
-            bulk_s2g(esave, sA + q * PAIR_BYTES, PAIR_BYTES);
-            bulk_s2g(esave + SLAB_BYTES, sA + SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+            bulk_s2g_hint(esave, sA + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
+            bulk_s2g_hint(esave + SLAB_BYTES, sA + SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
             bulk_commit();
           }
         }
@@ -329,6 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
             mbar_wait(bar.acc(h), ph);
             if (h == 0) { PROF_ADD(t_acc0, t0); } else { PROF_ADD(t_acc1, t0); }
           }
+          ESTAMP();
           tcgen05_fence_after();
           uint32_t accA[32], accB[32];
           tmem_ld32(tm_row + h * 256, accA);
@@ -349,17 +365,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
                     make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
             fence_proxy_async_smem();
+            if (!last) {   // hand the slabs to the MMA issuer first: the stores below are off the critical path
+              tcgen05_fence_before();
+              arrive_ready(0);
+            }
             if (TRAIN) {
               named_bar_sync(2 + q, 64);
               if (ch == 0 && lane == 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bulk_s2g(hsave + j * SLAB_BYTES + q * PAIR_BYTES, sA + j * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+                for (int j = 0; j < 4; ++j) bulk_s2g_hint(hsave + j * SLAB_BYTES + q * PAIR_BYTES, sA + j * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
                 bulk_commit();
               }
-            }
-            if (!last) {
-              tcgen05_fence_before();
-              arrive_ready(0);
             }
           }
 #pragma unroll
@@ -382,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
 #endif
               pk[i / 2] = pack_bf16x2(s0, s1); pk[i / 2 + 1] = pack_bf16x2(s2, s3);
-              if (TRAIN) cq[i / 4] = cosq_pack4(__cosf(v0), __cosf(v1), __cosf(v2), __cosf(v3));
+              if (TRAIN) cq[i / 4] = cosq_pack4(cosq_enc(v0), cosq_enc(v1), cosq_enc(v2), cosq_enc(v3));   // cos(pre) for the backward
               if (last) {   // fused output layer: out = W_out h + b_out
                 const float4 wa = *reinterpret_cast<const float4 *>(wout_s + col0 + i);
                 const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + col0 + i);
@@ -405,16 +421,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                   *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
                       make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 fence_proxy_async_smem();
-                if (TRAIN) {   // h_l for the weight gradients: the pair's 32 rows of this slab are one contiguous 4 KB block
-                  named_bar_sync(2 + q, 64);
-                  if (ch == 0 && lane == 0) {
-                    bulk_s2g(hsave + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
-                    bulk_commit();
-                  }
-                }
                 if (!last) {
                   tcgen05_fence_before();
                   arrive_ready(1 + j);
+                }
+                if (TRAIN) {   // h_l for the weight gradients: the pair's 32 rows of this slab are one contiguous 4 KB block
+                  named_bar_sync(2 + q, 64);
+                  if (ch == 0 && lane == 0) {
+                    bulk_s2g_hint(hsave + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
+                    bulk_commit();
+                  }
                 }
               }
             }

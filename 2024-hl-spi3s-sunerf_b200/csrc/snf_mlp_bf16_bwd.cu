@@ -94,6 +94,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     // pre-activation images about one layer ahead of the epilogue that multiplies by their cosine
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      const uint64_t keep = l2_policy_evict_last();
       auto pre_img = [&](int tile, int l) { return p.save_pre + ((int64_t)tile * NH + l) * C_BYTES; };
       {
         const int tile = pair * 2 + (int)rank;
@@ -109,7 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           for (int b = 0; b < 16; ++b) {
             mbar_wait(bar.empty(s), ph ^ 1);
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
-            bulk_g2s(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s));
+            bulk_g2s_hint(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s), keep);
             if (l >= 2) {
               if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * (C_BYTES / 8), C_BYTES / 8);
             } else if (next_tile < p.num_tiles) {   // l == 1: the next tile's first two images
@@ -191,12 +192,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       return cosq_get(w, i & 3);
     };
     // slab sl of the A image is complete for this pair's 32 rows: hand it to the MMAs and store it for the wgrad
-    auto publish = [&](uint8_t *dimg, int sl0, int nsl) {
+    const uint64_t stream_pol = l2_policy_evict_first();
+    // hand complete slabs to the MMA issuer first (ready barrier k, or none), then store them for the wgrad
+    auto publish = [&](uint8_t *dimg, int sl0, int nsl, int k) {
       fence_proxy_async_smem();
+      if (k >= 0) { tcgen05_fence_before(); arrive_ready(k); }
       named_bar_sync(2 + q, 64);
       if (ch == 0 && lane == 0) {
         for (int sl = sl0; sl < sl0 + nsl; ++sl)
-          bulk_s2g(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES);
+          bulk_s2g_hint(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
         bulk_commit();
       }
     };
@@ -234,10 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * cos_of(pv, 8 * c + 6), (gg.x * wa1.w + gg.y * wb1.w) * cos_of(pv, 8 * c + 7));
             *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) = o;
           }
-          publish(d7, sl, 1);
-          tcgen05_fence_before();
-          if (sl == 3) arrive_ready(0);
-          if (sl >= 4) arrive_ready(sl - 3);
+          publish(d7, sl, 1, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
         }
       }
 #pragma unroll 1
@@ -264,8 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
               for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
                     make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
-            publish(dprev, 0, 4);
-            if (!last) { tcgen05_fence_before(); arrive_ready(0); }
+            publish(dprev, 0, 4, last ? -1 : 0);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -295,9 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
               for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-              publish(dprev, sl, 1);
-              tcgen05_fence_before();
-              if (!last) arrive_ready(1 + j);
+              publish(dprev, sl, 1, last ? -1 : 1 + j);
             }
           }
         }

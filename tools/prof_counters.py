@@ -34,6 +34,12 @@ L.snf_debug_trace.argtypes = [ctypes.c_void_p]
 assert L.snf_debug_trace(tb) == 0
 t = np.array(tb, dtype=np.int64).reshape(4, 512)
 t0 = t[1, 0]
-print('blk: producer saw empty | issuer starts full-wait | issuer full-wait done   (cycles since first, CTA 0 second tile)')
+t0 = t[1, 0]
+print('issuer / producer trace (cycles since the first full-wait of CTA 0, second tile)')
+print('blk: producer saw empty | issuer starts full-wait | done')
 for i in range(0, 116):
     print(f'{i:4d} {t[0, i] - t0:9d} {t[1, i] - t0:9d} {t[2, i] - t0:9d}  wait {t[2, i] - t[1, i]:6d}')
+print('epilogue warp 0 stamps: per layer [acc0 done, acc1 done, ready0 arrive, ready1..4 arrive] (enc ready first)')
+e = t[3]
+n = int((e != 0).sum())
+print(' '.join(str(int(x - t0)) for x in e[:n]))
