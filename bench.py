@@ -43,7 +43,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -150,7 +150,7 @@ def cpu_baseline(sample_rays=256):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
@@ -182,17 +182,17 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
 
     # ---- CUDA-event instrumentation of the dominant kernel group (field-network forward + backward)
-    mlp_events = []
+    mlp_events = []            # (start, stop, 'fwd' | 'bwd') on torch's current stream = the stream the kernels launch on
     _fwd, _bwd = ops.mlp_forward, ops.mlp_backward
 
-    def timed(fn):
+    def timed(fn, tag):
         def w(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); r = fn(*a, **k); e1.record()
-            mlp_events.append((e0, e1))
+            mlp_events.append((e0, e1, tag))
             return r
         return w
-    ops.mlp_forward, ops.mlp_backward = timed(_fwd), timed(_bwd)
+    ops.mlp_forward, ops.mlp_backward = timed(_fwd, 'fwd'), timed(_bwd, 'bwd')
 
     def step_resident():
         t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
@@ -231,7 +231,9 @@ def main():
     l0 = ops.launch_count()
     ms = timed_loop(step_resident, args.steps)
     launches = ops.launch_count() - l0
-    mlp_ms = sum(a.elapsed_time(bb) for a, bb in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
+    mlp_ms = sum(a.elapsed_time(bb) for a, bb, _ in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
+    fwd_ms = sum(a.elapsed_time(bb) for a, bb, t in mlp_events if t == 'fwd') / max(1, args.steps)
+    bwd_ms = mlp_ms - fwd_ms
     ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
     for _ in range(2):
         step_e2e()
@@ -259,6 +261,10 @@ def main():
     e2e = N * world * args.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     achieved = N * FLOP_TRAIN_RAY / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    traffic = None             # DRAM bytes of the field-network kernels of one step, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+    if args.precision == 'bf16' and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('train_step_mlp_traffic_bytes')
     line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
@@ -268,12 +274,16 @@ def main():
             'gpu_launches': int(launches) * world,
             'roofline': {'bound': 'tensor', 'kernel': f'field-network MLP forward+backward ({args.precision})',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
-                         'traffic': None, 'peak_source': pk['src'] + ' (sustained cuBLAS bf16)',
+                         'traffic': traffic, 'peak_source': pk['src'] + ' (sustained cuBLAS bf16: the kernels run inside a long step)',
+                         'launches_per_step': 6 if args.precision == 'bf16' else None,
+                         'forward': {'ms_per_step': fwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_FWD_POINT / (fwd_ms * 1e-3) / 1e12},
+                         'backward': {'ms_per_step': bwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_BWD_POINT / (bwd_ms * 1e-3) / 1e12},
                          'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / (ms / args.steps),
                          'algorithmic_flop_per_step': N * FLOP_TRAIN_RAY},
             'render': {'metric': 'render_Msamples_per_s', 'value': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_render * 1e-3) / 1e6,
                        'unit': 'Msamples/s', 'rays_per_batch': RENDER_BATCH, 'ms_per_batch': ms_render,
-                       'tensor_frac': RENDER_BATCH * FLOP_RENDER_RAY / (ms_render * 1e-3) / 1e12 / pk['tflops']},
+                       'tensor_frac': RENDER_BATCH * FLOP_RENDER_RAY / (ms_render * 1e-3) / 1e12 / pk['tflops_burst'],
+                       'tensor_peak': pk['tflops_burst'], 'tensor_peak_source': pk['src'] + ' (burst cuBLAS bf16: a 3 ms forward timed alone)'},
             'clocks': clk}
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline()
