@@ -9,6 +9,7 @@ Drop-in surface (same names, constructor arguments, forward contracts and state_
                                                                DensityTemperatureRadiativeTransfer
     sunerf/train/scaling.py          -> sunerf_b200.trainer    ImageAsinhScaling
     Lightning training_step + optim  -> sunerf_b200.trainer    RayTrainer (ray-sharded, one NCCL all-reduce/step)
+    sunerf/evaluation/loader.py      -> sunerf_b200.image_render  ObserverRenderer.render_observer_image (rays on device)
 
 The directory is named after the upstream repo (`2024-hl-spi3s-sunerf_b200`, not a valid Python identifier);
 `import sunerf_b200` resolves to it through the small alias package at the repo root.
@@ -20,8 +21,9 @@ from .model import NeRF, NeRF_DT, EmissionModel, PositionalEncoding, Sine, Simpl
 from .sampling import StratifiedSampler, HierarchicalSampler
 from .rendering import SuNeRFRendering, EmissionRadiativeTransfer, DensityTemperatureRadiativeTransfer
 from .trainer import RayTrainer, ImageAsinhScaling
-from . import rays, parallel
+from . import rays, parallel, image_render
+from .image_render import ObserverRenderer
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
            'StratifiedSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
-           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling']
+           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer']

@@ -17,7 +17,7 @@ CSRC = os.path.join(_PKG, 'csrc')
 LIB_DIR = os.path.join(_PKG, 'lib')
 # SNF_LIB_NAME: developer-only, lets experiment builds (SNF_NVCC_EXTRA) live next to the product library
 LIB_PATH = os.path.join(LIB_DIR, os.environ.get('SNF_LIB_NAME', 'libsunerf_b200.so'))
-SOURCES = ['snf_sampling.cu', 'snf_composite.cu', 'snf_mlp_f32.cu', 'snf_mlp_bf16.cu', 'snf_mlp_bf16_bwd.cu',
+SOURCES = ['snf_sampling.cu', 'snf_rays.cu', 'snf_composite.cu', 'snf_mlp_f32.cu', 'snf_mlp_bf16.cu', 'snf_mlp_bf16_bwd.cu',
            'snf_optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
@@ -66,13 +66,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _c = ctypes
-_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+_P, _I, _L, _F, _D = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_double
 _PROTOS = {
     'snf_version': (_I, []),
     'snf_error_string': (_c.c_char_p, [_I]),
     'snf_launch_count': (_L, []),
     'snf_stratified_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
     'snf_hier_resample': (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
+    'snf_image_rays': (_I, [_P, _I, _I, _D, _D, _D, _D, _L, _L, _P, _P, _P]),
     'snf_make_query': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     'snf_mlp_ws_bytes': (_L, [_L, _I, _I, _I, _I]),
     'snf_mlp_fwd_f32': (_I, [_P, _L, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P]),

@@ -70,6 +70,29 @@ def hier_resample(z_vals, weights, u, cdf_in=None, want_inds: bool = False, want
     return new_z, z_comb, inds, cdf
 
 
+def image_rays(c2w, H: int, W: int, plate_arcsec: float, device, first: int = 0, count: Optional[int] = None,
+               center_pixel: Optional[Tuple[float, float]] = None):
+    """N1 - get_rays (sunerf/data/ray_sampling.py:7-36) on the device for the regular grid Tx=(j-cx)p, Ty=(i-cy)p.
+    c2w: the 4x4 (or 3x4) pose_spherical matrix on the HOST. Returns rays_o, rays_d [count,3] for pixels
+    [first, first+count) of the row-major H x W image."""
+    import numpy as np
+    m = np.ascontiguousarray(np.asarray(c2w, dtype=np.float32))
+    if m.shape not in ((4, 4), (3, 4)):
+        raise _lib.SnfError('image_rays: c2w must be 4x4 or 3x4')
+    count = H * W - first if count is None else count
+    cx, cy = ((W - 1) / 2, (H - 1) / 2) if center_pixel is None else center_pixel
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise _lib.SnfError('image_rays: sunerf_b200 kernels need a CUDA device (no CPU fallback exists)')
+    with torch.cuda.device(dev):
+        rays_o = torch.empty(count, 3, device=dev, dtype=torch.float32)
+        rays_d = torch.empty(count, 3, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().snf_image_rays(m.ctypes.data, H, W, float(plate_arcsec), float(np.pi / 180 / 3600), float(cx),
+                                             float(cy), int(first), int(count), rays_o.data_ptr(), rays_d.data_ptr(),
+                                             _stream()), 'snf_image_rays')
+    return rays_o, rays_d
+
+
 def make_query(rays_o, rays_d, z, times):
     """a3 - query[N,S,4] = (o + d*z, t) (sampling.py:100, base_tracing.py:64-65)."""
     rays_o, rays_d, z, times = _f32(rays_o, 'rays_o'), _f32(rays_d, 'rays_d'), _f32(z, 'z'), _f32(times, 'times')

@@ -48,6 +48,13 @@ int snf_hier_resample(const float *z_vals, const float *weights, const float *u,
                       int S, int n_new, float *new_z, float *z_comb, int64_t *inds, float *cdf_out, void *stream);
 
 /* ---- a3: query = cat(o + d*z, t), sunerf/rendering/base_tracing.py:64-65, 83-84; sampling.py:100 ---- */
+/* N1: observer image rays on the device.  Replaces get_rays (sunerf/data/ray_sampling.py:7-36) for the
+ * regular pixel grid Tx = (j - cx) * plate_arcsec * asec, Ty = (i - cy) * plate_arcsec * asec; pixels [first, first+count)
+ * of the row-major H x W image.  c2w_host: the pose_spherical matrix (coordinate_transformation.py:36-54), HOST memory,
+ * row-major with a row stride of 4 floats (3x4 or 4x4). */
+int snf_image_rays(const float *c2w_host, int H, int W, double plate_arcsec, double asec, double cx, double cy,
+                   int64_t first, int64_t count, float *rays_o, float *rays_d, void *stream);
+
 int snf_make_query(const float *rays_o, const float *rays_d, const float *z, const float *times, int64_t N, int S,
                    float *query /*[N,S,4]*/, void *stream);
 
