@@ -21,9 +21,10 @@ from .model import NeRF, NeRF_DT, EmissionModel, PositionalEncoding, Sine, Simpl
 from .sampling import StratifiedSampler, HierarchicalSampler
 from .rendering import SuNeRFRendering, EmissionRadiativeTransfer, DensityTemperatureRadiativeTransfer
 from .trainer import RayTrainer, ImageAsinhScaling
-from . import rays, parallel, image_render
+from . import rays, parallel, image_render, checkpoint, ray_store
+from .ray_store import RayStore
 from .image_render import ObserverRenderer
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
            'StratifiedSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
-           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer']
+           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore']
