@@ -193,71 +193,128 @@ __device__ __forceinline__ int dt_segment(const DtTables *t, float th) {
   return g;
 }
 
+// K6 layout: persistent CTAs (the response tables and their slopes are built once per CTA, not once per 4 rays),
+// one warp per ray, the ray register-resident as in K5.  The optical depth of channel c is kappa_c * B / 2 with
+//   B[k] = cumsum_k (z[k+1]-z[k]) (rho[k] + rho[k+1])        (cumulative_trapezoid of rho, :261)
+// so ONE double-precision scan per ray serves all C channels (the reference multiplies by kappa_c inside the sum;
+// factoring it out moves the result by ~1e-7 relative, the gate is 1e-5).
+template <int NCH>
+struct DtRay {
+  float z[NCH], rho[NCH], dxq[NCH], dzn[NCH], B[NCH];   // dzn[k] = z[k+1]-z[k]; B = 2 x cumulative trapezoid of rho
+  int seg[NCH];
+};
+
+// value of the next sample (lane + 1), crossing into the next chunk's lane 0
+template <int NCH>
+__device__ __forceinline__ void next_sample(const float (&v)[NCH], int lane, float (&nx)[NCH]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float dn = __shfl_down_sync(kFull, v[c], 1);
+    const float first_next = __shfl_sync(kFull, v[c + 1 < NCH ? c + 1 : c], 0);
+    nx[c] = lane < 31 ? dn : first_next;
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void prev_sample(const float (&v)[NCH], int lane, float (&pv)[NCH]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float up = __shfl_up_sync(kFull, v[c], 1);
+    const float last_prev = __shfl_sync(kFull, v[c > 0 ? c - 1 : c], 31);
+    pv[c] = lane > 0 ? up : last_prev;
+  }
+}
+
+template <int NCH>
+__device__ __forceinline__ void dt_ray_setup(DtRay<NCH> &r, const DtTables *tab, const float (&zr)[NCH],
+                                             const float2 (&v)[NCH], int lane, int S) {
+  float rn[NCH], zn[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    r.z[c] = zr[c];
+    r.rho[c] = expf(fmaxf(v[c].x, 0.f));                                      // :237
+    const float th = fmaxf(v[c].y, 0.f);                                      // :241
+    const int sg = (c * 32 + lane < S) ? dt_segment(tab, th) : -1;
+    r.seg[c] = sg;
+    r.dxq[c] = sg >= 0 ? fsub(th, tab->x[sg]) : 0.f;
+  }
+  next_sample<NCH>(r.rho, lane, rn);
+  next_sample<NCH>(r.z, lane, zn);
+  double carry = 0.0;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const bool ok = c * 32 + lane < S - 1;
+    r.dzn[c] = ok ? fsub(zn[c], r.z[c]) : 0.f;
+    const double term = ok ? (double)fmul(r.dzn[c], fadd(r.rho[c], rn[c])) : 0.0;
+    const double inc = warp_incl_sum(term, lane) + carry;
+    r.B[c] = (float)inc;
+    carry = __shfl_sync(kFull, inc, 31);
+  }
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(kRayWarps * 32)
     composite_dt_fwd_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
                             const float *__restrict__ wavelengths, int64_t N, int S, int C,
                             const float *__restrict__ log_abs, const float *__restrict__ vol_c,
                             const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
                             float *__restrict__ image, float *__restrict__ weights, float *__restrict__ regq) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  DtTables *tab = reinterpret_cast<DtTables *>(smraw);
-  float *sm = reinterpret_cast<float *>(smraw + sizeof(DtTables));
-  dt_load_tables(tab, table_x, table_y, log_abs);
+  __shared__ DtTables tabs;
+  const DtTables *tab = &tabs;
+  dt_load_tables(&tabs, table_x, table_y, log_abs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
-  if (ray >= N) return;
-  float *zs = sm + (size_t)warp * 5 * S, *rho = zs + S, *dxq = rho + S, *tau = dxq + S;
-  int *seg = reinterpret_cast<int *>(tau + S);
   const float vc = vol_c[0];
-  double qsum = 0.0;
-  for (int j = lane; j < S; j += 32) {
-    zs[j] = z[ray * S + j];
-    const float2 v = inf[ray * S + j];
-    const float q = fmaxf(v.x, 0.f);
-    rho[j] = expf(q);                                                        // :237
-    const float th = fmaxf(v.y, 0.f);                                        // :241
-    const int s = dt_segment(tab, th);
-    seg[j] = s;
-    dxq[j] = s >= 0 ? fsub(th, tab->x[s]) : 0.f;
-    regq[ray * S + j] = q;                                                   // :271
-    qsum += (double)q;
-  }
-  const float den = fadd((float)warp_sum(qsum), 1e-10f);
-  __syncwarp();
-  for (int j = lane; j < S; j += 32) weights[ray * S + j] = fdiv(fmaxf(inf[ray * S + j].x, 0.f), den);   // :268-269
-  for (int c = 0; c < C; ++c) {
-    const int k = dt_channel(wavelengths[ray * C + c]);
-    if (k < 0) {   // channel absent: response and absorption stay 0 (:243, :251) -> image 0 * vol_c * F
-      if (lane == 0) image[ray * C + c] = fmul(fmul(0.f, vc), F);
-      continue;
+  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += (int64_t)gridDim.x * kRayWarps) {
+    float zr[NCH];
+    float2 v[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = c * 32 + lane;
+      zr[c] = j < S ? __ldcs(z + ray * S + j) : 0.f;
+      v[c] = j < S ? __ldcs(inf + ray * S + j) : make_float2(0.f, 0.f);
     }
-    const float kap = tab->kappa[k];
-    double carry = 0.0;
-    for (int base = 0; base < S - 1; base += 32) {
-      const int j = base + lane;
-      const bool ok = j < S - 1;
-      double term = 0.0;
-      if (ok)   // cumulative_trapezoid: cumsum(dx*(left+right))/2   :261
-        term = (double)fmul(fsub(zs[j + 1], zs[j]), fadd(fmul(rho[j], kap), fmul(rho[j + 1], kap)));
-      const double inc = warp_incl_sum(term, lane) + carry;
-      if (ok) {
-        const float A = fdiv((float)inc, 2.f);
-        const int s = seg[j];
-        const float R = s >= 0 ? fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s])) : 0.f;
-        const float em = fmul(fmul(rho[j], rho[j]), R);                      // :263
-        tau[j] = fmul(expf(-A), em);                                         // :264
+    double qsum = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = c * 32 + lane;
+      const float q = fmaxf(v[c].x, 0.f);
+      if (j < S) { __stcs(regq + ray * S + j, q); qsum += (double)q; }         // :271
+    }
+    const float den = fadd((float)warp_sum(qsum), 1e-10f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = c * 32 + lane;
+      if (j < S) __stcs(weights + ray * S + j, fdiv(fmaxf(v[c].x, 0.f), den));  // :268-269
+    }
+    DtRay<NCH> r;
+    dt_ray_setup<NCH>(r, tab, zr, v, lane, S);
+    for (int c = 0; c < C; ++c) {
+      const int k = dt_channel(wavelengths[ray * C + c]);
+      if (k < 0) {   // channel absent: response and absorption stay 0 (:243, :251) -> image 0 * vol_c * F
+        if (lane == 0) image[ray * C + c] = fmul(fmul(0.f, vc), F);
+        continue;
       }
-      carry = __shfl_sync(kFull, inc, 31);
+      const float kap = tab->kappa[k];
+      float tau[NCH], tn[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float A = fmul(fmul(kap, r.B[ch]), 0.5f);                         // :261
+        const int sg = r.seg[ch];
+        const float R = sg >= 0 ? fadd(tab->y[k][sg], fmul(r.dxq[ch], tab->slope[k][sg])) : 0.f;
+        const float em = fmul(fmul(r.rho[ch], r.rho[ch]), R);                   // :263
+        tau[ch] = (ch * 32 + lane < S - 1) ? fmul(expf(-A), em) : 0.f;          // :264
+      }
+      next_sample<NCH>(tau, lane, tn);
+      double part = 0.0;   // trapezoid over z[0..S-2]: sum(dx*(left+right))/2   :265
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 + lane < S - 2) part += (double)fmul(r.dzn[ch], fadd(tau[ch], tn[ch]));
+      const float J = fdiv((float)warp_sum(part), 2.f);
+      if (lane == 0) image[ray * C + c] = fmul(fmul(J, vc), F);
     }
-    __syncwarp();
-    double part = 0.0;   // trapezoid over z[0..S-2]: sum(dx*(left+right))/2   :265
-    for (int j = lane; j < S - 2; j += 32) part += (double)fmul(fsub(zs[j + 1], zs[j]), fadd(tau[j], tau[j + 1]));
-    const float J = fdiv((float)warp_sum(part), 2.f);
-    if (lane == 0) image[ray * C + c] = fmul(fmul(J, vc), F);
-    __syncwarp();
   }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(kRayWarps * 32)
     composite_dt_bwd_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
                             const float *__restrict__ wavelengths, int64_t N, int S, int C,
@@ -265,110 +322,113 @@ __global__ void __launch_bounds__(kRayWarps * 32)
                             const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
                             const float *__restrict__ g_image, const float *__restrict__ g_regq,
                             float2 *__restrict__ g_inf, float *__restrict__ g_log_abs, float *__restrict__ g_vol_c) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  DtTables *tab = reinterpret_cast<DtTables *>(smraw);
-  float *blk_acc = reinterpret_cast<float *>(smraw + sizeof(DtTables));   // [8]: 7 kappa grads + vol_c grad
-  float *sm = blk_acc + 8;
+  __shared__ DtTables tabs;
+  __shared__ float blk_acc[8];   // 7 kappa grads + vol_c grad of this CTA's rays
+  const DtTables *tab = &tabs;
   if (threadIdx.x < 8) blk_acc[threadIdx.x] = 0.f;
-  dt_load_tables(tab, table_x, table_y, log_abs);
+  dt_load_tables(&tabs, table_x, table_y, log_abs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
-  if (ray < N) {
-    float *zs = sm + (size_t)warp * 9 * S, *rho = zs + S, *dxq = rho + S, *tau = dxq + S, *eA = tau + S,
-          *Gs = eA + S, *drho = Gs + S, *dth = drho + S;
-    int *seg = reinterpret_cast<int *>(dth + S);
-    const float vc = vol_c[0];
-    for (int j = lane; j < S; j += 32) {
-      zs[j] = z[ray * S + j];
-      const float2 v = inf[ray * S + j];
-      rho[j] = expf(fmaxf(v.x, 0.f));
-      const float th = fmaxf(v.y, 0.f);
-      const int s = dt_segment(tab, th);
-      seg[j] = s;
-      dxq[j] = s >= 0 ? fsub(th, tab->x[s]) : 0.f;
-      drho[j] = 0.f;
-      dth[j] = 0.f;
+  const float vc = vol_c[0];
+  float acc_k[SNF_N_AIA], gvc = 0.f;
+#pragma unroll
+  for (int k = 0; k < SNF_N_AIA; ++k) acc_k[k] = 0.f;
+  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += (int64_t)gridDim.x * kRayWarps) {
+    float zr[NCH], greg[NCH];
+    float2 v[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = c * 32 + lane;
+      zr[c] = j < S ? __ldcs(z + ray * S + j) : 0.f;
+      v[c] = j < S ? __ldcs(inf + ray * S + j) : make_float2(0.f, 0.f);
+      greg[c] = (g_regq != nullptr && j < S) ? __ldcs(g_regq + ray * S + j) : 0.f;
     }
-    __syncwarp();
-    float gvc = 0.f;
+    DtRay<NCH> r;
+    dt_ray_setup<NCH>(r, tab, zr, v, lane, S);
+    // trapezoid node weights over z[0..S-2]: w_k = (dz_{k-1} [k>=1] + dz_k [k<=S-3]) / 2
+    float dzp[NCH], wk[NCH], drho[NCH], dth[NCH], dB[NCH];
+    prev_sample<NCH>(r.dzn, lane, dzp);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = ch * 32 + lane;
+      wk[ch] = j <= S - 2 ? 0.5f * ((j >= 1 ? dzp[ch] : 0.f) + (j <= S - 3 ? r.dzn[ch] : 0.f)) : 0.f;
+      drho[ch] = dth[ch] = dB[ch] = 0.f;
+    }
     for (int c = 0; c < C; ++c) {
       const int k = dt_channel(wavelengths[ray * C + c]);
       if (k < 0) continue;   // image is the constant 0: no gradient to anything but vol_c (0 * F)
       const float kap = tab->kappa[k];
       const float gi = g_image[ray * C + c];
-      double carry = 0.0;
-      for (int base = 0; base < S - 1; base += 32) {
-        const int j = base + lane;
-        const bool ok = j < S - 1;
-        double term = 0.0;
-        if (ok) term = (double)fmul(fsub(zs[j + 1], zs[j]), fadd(fmul(rho[j], kap), fmul(rho[j + 1], kap)));
-        const double inc = warp_incl_sum(term, lane) + carry;
-        if (ok) {
-          const float A = fdiv((float)inc, 2.f);
-          const int s = seg[j];
-          const float R = s >= 0 ? fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s])) : 0.f;
-          const float e = expf(-A);
-          eA[j] = e;
-          tau[j] = fmul(e, fmul(fmul(rho[j], rho[j]), R));
-        }
-        carry = __shfl_sync(kFull, inc, 31);
+      float tau[NCH], eA[NCH], Rr[NCH], tn[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float A = fmul(fmul(kap, r.B[ch]), 0.5f);
+        const int sg = r.seg[ch];
+        Rr[ch] = sg >= 0 ? fadd(tab->y[k][sg], fmul(r.dxq[ch], tab->slope[k][sg])) : 0.f;
+        const bool ok = ch * 32 + lane < S - 1;
+        eA[ch] = ok ? expf(-A) : 0.f;
+        tau[ch] = ok ? fmul(eA[ch], fmul(fmul(r.rho[ch], r.rho[ch]), Rr[ch])) : 0.f;
       }
-      __syncwarp();
+      next_sample<NCH>(tau, lane, tn);
       double part = 0.0;
-      for (int j = lane; j < S - 2; j += 32) part += (double)fmul(fsub(zs[j + 1], zs[j]), fadd(tau[j], tau[j + 1]));
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 + lane < S - 2) part += (double)fmul(r.dzn[ch], fadd(tau[ch], tn[ch]));
       const float J = fdiv((float)warp_sum(part), 2.f);
       gvc += gi * J * F;                       // I = J * vol_c * F
       const float Gc = gi * vc * F;            // dL/dJ
-      // dL/dA_k = -Gc w_k tau_k, suffix-summed into G_j = sum_{k>=j} dL/dA_k, k in [0, S-2]
-      double rcarry = 0.0;
-      const int n = S - 1, nchunk = (n + 31) / 32;
-      for (int ch = nchunk - 1; ch >= 0; --ch) {
-        const int j = ch * 32 + lane;
-        const bool ok = j < n;
-        double dA = 0.0;
-        if (ok) {
-          const float wk = 0.5f * ((j >= 1 ? zs[j] - zs[j - 1] : 0.f) + (j <= S - 3 ? zs[j + 1] - zs[j] : 0.f));
-          dA = -(double)Gc * wk * tau[j];
+      float dk = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        // dL/dA_k = -Gc w_k tau_k with A = kappa B / 2: dL/dB_k += kappa/2 dL/dA_k ; dL/dkappa += B_k/2 dL/dA_k
+        const float dA = -Gc * wk[ch] * tau[ch];
+        dB[ch] += 0.5f * kap * dA;
+        dk += 0.5f * r.B[ch] * dA;
+        const float dem = Gc * wk[ch] * eA[ch];   // dL/d em_j
+        if (r.seg[ch] >= 0) {
+          drho[ch] += dem * 2.f * r.rho[ch] * Rr[ch];
+          dth[ch] += dem * r.rho[ch] * r.rho[ch] * tab->slope[k][r.seg[ch]];
         }
-        const double suf = warp_suffix_sum(dA, lane) + rcarry;
-        if (ok) Gs[j] = (float)suf;
-        rcarry = __shfl_sync(kFull, suf, 0);
       }
-      __syncwarp();
-      float dkap = 0.f;
-      for (int j = lane; j < S; j += 32) {
-        // absorption_j enters A_k (k>=j) through dx_j/2 and A_k (k>=j-1) through dx_{j-1}/2
-        float dabs = 0.f;
-        if (j <= S - 2) dabs += 0.5f * (zs[j + 1] - zs[j]) * Gs[j];
-        if (j >= 1) dabs += 0.5f * (zs[j] - zs[j - 1]) * Gs[j - 1];
-        float dr = dabs * kap;
-        dkap += dabs * rho[j];
-        if (j <= S - 2) {
-          const float wk = 0.5f * ((j >= 1 ? zs[j] - zs[j - 1] : 0.f) + (j <= S - 3 ? zs[j + 1] - zs[j] : 0.f));
-          const float dem = Gc * wk * eA[j];   // dL/d em_j
-          const int s = seg[j];
-          if (s >= 0) {
-            const float R = fadd(tab->y[k][s], fmul(dxq[j], tab->slope[k][s]));
-            dr += dem * 2.f * rho[j] * R;
-            dth[j] += dem * rho[j] * rho[j] * tab->slope[k][s];
-          }
-        }
-        drho[j] += dr;
-      }
-      dkap = warp_sum_f(dkap) * tab->kappa_on[k];
-      if (lane == 0 && dkap != 0.f) atomicAdd(&blk_acc[k], dkap);
-      __syncwarp();
+      dk *= tab->kappa_on[k];
+#pragma unroll
+      for (int kk = 0; kk < SNF_N_AIA; ++kk) acc_k[kk] += (kk == k) ? dk : 0.f;   // static indices: stays in registers
     }
-    gvc = 0.f + gvc;
-    if (lane == 0) atomicAdd(&blk_acc[7], gvc);
-    for (int j = lane; j < S; j += 32) {
-      const float2 v = inf[ray * S + j];
-      float2 o;
-      o.x = v.x > 0.f ? drho[j] * rho[j] + (g_regq != nullptr ? g_regq[ray * S + j] : 0.f) : 0.f;
-      o.y = v.y > 0.f ? dth[j] : 0.f;
-      g_inf[ray * S + j] = o;
+    // G_i = sum_{k>=i} dL/dB_k = dL/d term_i, term_i = dz_i (rho_i + rho_{i+1}): one suffix scan for all channels
+    float G[NCH], Gp[NCH];
+    float rcarry = 0.f;
+#pragma unroll
+    for (int ch = NCH - 1; ch >= 0; --ch) {
+      float suf = dB[ch];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float n = __shfl_down_sync(kFull, suf, d);
+        if (lane + d < 32) suf += n;
+      }
+      suf += rcarry;
+      G[ch] = suf;
+      rcarry = __shfl_sync(kFull, suf, 0);
+    }
+    prev_sample<NCH>(G, lane, Gp);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = ch * 32 + lane;
+      if (j < S) {
+        float dr = drho[ch];
+        if (j <= S - 2) dr += r.dzn[ch] * G[ch];
+        if (j >= 1) dr += dzp[ch] * Gp[ch];
+        float2 o;
+        o.x = v[ch].x > 0.f ? dr * r.rho[ch] + greg[ch] : 0.f;
+        o.y = v[ch].y > 0.f ? dth[ch] : 0.f;
+        __stcs(g_inf + ray * S + j, o);
+      }
     }
   }
+#pragma unroll
+  for (int k = 0; k < SNF_N_AIA; ++k) {
+    const float t = warp_sum_f(acc_k[k]);
+    if (lane == 0 && t != 0.f) atomicAdd(&blk_acc[k], t);
+  }
+  if (lane == 0 && gvc != 0.f) atomicAdd(&blk_acc[7], gvc);
   __syncthreads();
   if (threadIdx.x < 7 && blk_acc[threadIdx.x] != 0.f) atomicAdd(&g_log_abs[threadIdx.x], blk_acc[threadIdx.x]);
   if (threadIdx.x == 7 && blk_acc[7] != 0.f) atomicAdd(g_vol_c, blk_acc[7]);
@@ -526,10 +586,17 @@ extern "C" int snf_composite_dt_fwd(const float *inferences, const float *z, con
   if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
   if (S > 256 || C > 8) return SNF_E_SHAPE;
   if (N == 0) return 0;
-  const size_t smem = sizeof(DtTables) + (size_t)kRayWarps * 5 * S * sizeof(float);
-  composite_dt_fwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2 *>(inferences), z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F,
-      image, weights, regq);
+  int64_t nblk = ceil_div64(N, kRayWarps);
+  if (nblk > 148 * 16) nblk = 148 * 16;             // persistent CTAs: the tables are built once per CTA
+  const float2 *inf2 = reinterpret_cast<const float2 *>(inferences);
+#define SNF_LAUNCH(NCH) \
+  composite_dt_fwd_kernel<NCH><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
+      inf2, z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F, image, weights, regq)
+  switch ((S + 31) / 32) {
+    case 1: SNF_LAUNCH(1); break; case 2: SNF_LAUNCH(2); break; case 3: SNF_LAUNCH(3); break; case 4: SNF_LAUNCH(4); break;
+    case 5: SNF_LAUNCH(5); break; case 6: SNF_LAUNCH(6); break; case 7: SNF_LAUNCH(7); break; default: SNF_LAUNCH(8); break;
+  }
+#undef SNF_LAUNCH
   count_launch();
   return launch_status();
 }
@@ -545,15 +612,18 @@ extern "C" int snf_composite_dt_bwd(const float *inferences, const float *z, con
   if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
   if (S > 256 || C > 8) return SNF_E_SHAPE;
   if (N == 0) return 0;
-  const size_t smem = sizeof(DtTables) + 8 * sizeof(float) + (size_t)kRayWarps * 9 * S * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(composite_dt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
+  int64_t nblk = ceil_div64(N, kRayWarps);
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  const float2 *inf2 = reinterpret_cast<const float2 *>(inferences);
+  float2 *g2 = reinterpret_cast<float2 *>(g_inferences);
+#define SNF_LAUNCH(NCH) \
+  composite_dt_bwd_kernel<NCH><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
+      inf2, z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F, g_image, g_regq, g2, g_log_abs, g_vol_c)
+  switch ((S + 31) / 32) {
+    case 1: SNF_LAUNCH(1); break; case 2: SNF_LAUNCH(2); break; case 3: SNF_LAUNCH(3); break; case 4: SNF_LAUNCH(4); break;
+    case 5: SNF_LAUNCH(5); break; case 6: SNF_LAUNCH(6); break; case 7: SNF_LAUNCH(7); break; default: SNF_LAUNCH(8); break;
   }
-  composite_dt_bwd_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2 *>(inferences), z, wavelengths, N, S, C, log_abs, vol_c, table_x, table_y, F,
-      g_image, g_regq, reinterpret_cast<float2 *>(g_inferences), g_log_abs, g_vol_c);
+#undef SNF_LAUNCH
   count_launch();
   return launch_status();
 }

@@ -591,11 +591,20 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   }
   int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
   num_tiles = (num_tiles + 1) / 2 * 2;   // CTA pairs; the workspace is sized for the padding tile
-  // gradients are accumulated with atomics: clear them first (ABI: overwritten)
-  const int64_t wsz[9] = {512 * 84, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 2 * 512};
-  for (int l = 0; l <= bf::NH; ++l) {
-    cudaMemsetAsync(gW[l], 0, wsz[l] * 4, st);
-    cudaMemsetAsync(gB[l], 0, (l < bf::NH ? 512 : 2) * 4, st);
+  // gradients are accumulated with atomics: clear them first (ABI: overwritten).  The trainer hands views of one flat
+  // buffer, so adjacent (or alignment-padded) ranges are merged: normally a single memset instead of 18.
+  {
+    const int64_t wsz[9] = {512 * 84, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 512 * 512, 2 * 512};
+    uint8_t *lo = nullptr, *hi = nullptr;
+    auto flush = [&]() { if (lo != nullptr) cudaMemsetAsync(lo, 0, (size_t)(hi - lo), st); lo = hi = nullptr; };
+    auto add = [&](float *ptr, int64_t n) {
+      uint8_t *a = reinterpret_cast<uint8_t *>(ptr), *b = a + n * 4;
+      if (lo != nullptr && a >= hi && a - hi < 16) { hi = b; return; }   // contiguous up to the 16-byte segment padding
+      flush();
+      lo = a; hi = b;
+    };
+    for (int l = 0; l <= bf::NH; ++l) { add(gW[l], wsz[l]); add(gB[l], l < bf::NH ? 512 : 2); }
+    flush();
   }
   bf::DgradParams dp{};
   dp.g = reinterpret_cast<const float2 *>(grad_out);
