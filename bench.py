@@ -252,6 +252,16 @@ def main():
         render_once()
     ms_render = timed_loop(render_once, max(3, args.steps // 2)) / max(3, args.steps // 2)
 
+    # ---- full-image novel view (render_mhd.yaml at 1024^2): pose -> rays generated on the device ->
+    #      batched render -> image assembled on the device; this rank's share of the rows, no collective
+    renderer = s.ObserverRenderer(rend, (1024, 1024), plate_arcsec=2.4)
+    rows = s.parallel.shard_rows(1024, rank, world)
+
+    def image_once():
+        return renderer.render_observer_image(0.05, 1.0, 3.0, batch_size=RENDER_BATCH, rows=rows, as_numpy=False)
+    renderer.render_observer_image(0.05, 1.0, 3.0, batch_size=RENDER_BATCH, rows=slice(0, 16), as_numpy=False)   # warm-up
+    ms_image = timed_loop(image_once, 1)
+
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -283,7 +293,10 @@ def main():
             'render': {'metric': 'render_Msamples_per_s', 'value': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_render * 1e-3) / 1e6,
                        'unit': 'Msamples/s', 'rays_per_batch': RENDER_BATCH, 'ms_per_batch': ms_render,
                        'tensor_frac': RENDER_BATCH * FLOP_RENDER_RAY / (ms_render * 1e-3) / 1e12 / pk['tflops_burst'],
-                       'tensor_peak': pk['tflops_burst'], 'tensor_peak_source': pk['src'] + ' (burst cuBLAS bf16: a 3 ms forward timed alone)'},
+                       'tensor_peak': pk['tflops_burst'], 'tensor_peak_source': pk['src'] + ' (burst cuBLAS bf16: a 3 ms forward timed alone)',
+                       'image_1024': {'ms': ms_image, 'Msamples_per_s': 1024 * 1024 * (S_COARSE + S_FINE) / (ms_image * 1e-3) / 1e6,
+                                      'what': 'ObserverRenderer.render_observer_image, 1024x1024 pixels, rays generated on the '
+                                              'device, rows sharded over ranks, no collective'}},
             'clocks': clk}
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline()

@@ -365,6 +365,34 @@ def test_dt_training_gradients_autograd():
     _grad_checks(g, 'fine_model', r.fine_model)
 
 
+def test_dt_ray_trainer_bf16_matches_fp32():
+    """Density-temperature path (DT_2012_11.yaml: NeRF_DT + AIA response head, STEREO-masked channels) on the fast
+    training path in bf16-MLP mode against the fp32 mode: intensities 1e-2, gradients like the emission case."""
+    import sunerf_b200 as s
+    g, a, N = _dt_inputs()
+    trainers = []
+    for precision in ('fp32', 'bf16'):
+        torch.manual_seed(int(g['seed']))
+        r = s.DensityTemperatureRadiativeTransfer(Rs_per_ds=1, model=s.NeRF_DT, pixel_intensity_factor=1e17,
+                                                  model_config={'precision': precision}).cuda()
+        with torch.no_grad():
+            for i, c in enumerate(orc.AIA_CHANNELS):
+                r.coarse_model.log_absortpion[str(c)].fill_(float(g['log_abs_c'][i]))
+                r.fine_model.log_absortpion[str(c)].fill_(float(g['log_abs_f'][i]))
+        trainers.append(s.RayTrainer(r))
+    args = (t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['target']), t(g['wavelengths']))
+    a32 = trainers[0].step(*args, t_rand=t(g['t_rand']))
+    a16 = trainers[1].step(*args, t_rand=t(g['t_rand']))
+    assert abs(a32['losses'][0].item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    ref = a32['fine_image']
+    # exp(2 ln rho) doubles the relative error of the raw outputs: 2e-2 on the DT intensities in bf16 mode
+    assert ((a16['fine_image'] - ref).abs() <= 2 * INT_TOL_BF16 * ref.abs() + 1e-12).all()
+    cos = torch.nn.functional.cosine_similarity(trainers[0].flat_grad.double(), trainers[1].flat_grad.double(), dim=0).item()
+    assert cos > 0.995, cos
+    assert abs(a32['grad_norm'].item() - a16['grad_norm'].item()) <= 5e-2 * a32['grad_norm'].item()
+    trainers[1].check_finite()
+
+
 def test_ray_trainer_matches_oracle_step():
     """Fast path (no autograd): gradients equal the golden ones and one clip+Adam step equals the oracle's."""
     import sunerf_b200 as s
