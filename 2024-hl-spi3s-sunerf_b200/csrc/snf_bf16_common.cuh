@@ -20,25 +20,12 @@ constexpr int C_BYTES = TILE_M * D;          // 64 KB: cos(pre) of one tile and 
 constexpr int NCHUNK = 256;                  // output features per MMA / per weight block
 constexpr int WBLK_BYTES = NCHUNK * 128;     // weight block: 256 output features x 64 k = 32 KB
 constexpr int WHALF_BYTES = WBLK_BYTES / 2;  // each CTA of the pair streams half of every block: 16 KB
-constexpr int NSTAGE_TRAIN = 4;              // weight ring depth (x 16 KB per CTA) next to the 32 KB staging area
-constexpr int NSTAGE_INFER = 6;              // inference needs no staging: deeper ring
-constexpr int NSTAGE_MAX = 6;
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_EPI = N_EPI_WARPS * 32;      // 256 epilogue threads: (row, column half)
 constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2-3 idle;
 constexpr int NTHREADS = 128 + N_EPI;        // warpgroups 1-2 (warps 4..11): epilogue.  Registers are re-balanced with setmaxnreg:
 constexpr int REGS_CTRL = 40, REGS_EPI = 232;   // per SM sub-partition 1 control warp + 2 epilogue warps: 40 + 2 x 232 <= 512
-constexpr int STG_WARP_BYTES = 32 * 128;     // per-warp staging: 32 rows of one 64-column slab = 4 KB (contiguous in an image)
-constexpr int STG_BYTES = N_EPI_WARPS * STG_WARP_BYTES;
 constexpr int BIAS_BYTES = D * 4;
-// shared memory: [A image 128 KB][weight ring 96 KB = 6 stages, or 4 stages + 32 KB staging][bias 2 KB][barriers];
-// the base must be 1024-aligned
-constexpr int OFF_RING = A_BYTES;
-constexpr int OFF_STG = OFF_RING + NSTAGE_TRAIN * WHALF_BYTES;   // training only (overlays ring stages 4,5)
-constexpr int OFF_BIAS = OFF_RING + NSTAGE_MAX * WHALF_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(OFF_STG + STG_BYTES <= OFF_BIAS, "staging must fit behind the 4-stage ring");
 
 constexpr int FWD_BLOCKS = 2 * 2 + 7 * 16;   // forward weight blocks: layer 0 (2 n-halves x 2 k-slabs) + 7 x (2 x 8)
 constexpr int WT_BLOCKS = 7 * 16;            // W^T blocks for the dgrad chain (layers 1..7)
@@ -72,22 +59,7 @@ __device__ __forceinline__ float cosq_get(uint32_t wx, int b) {
   return (__uint_as_float(f) - 8388736.f) * (1.f / 127.f);
 }
 
-// Barrier block (8 bytes each) inside [OFF_BAR, OFF_BAR + 256)
-//   full[s]   : this CTA's half of stage s has landed (TMA complete_tx); on the LEADER it additionally counts one
-//               remote arrival from the peer's relay thread, so the MMA issuer waits on a single barrier per stage
-//               (the peer's relay waits on the peer's own full[s], count 1, then arrives remotely)
-//   empty[s]  : stage consumed (multicast tcgen05.commit from the leader), or released by the epilogue (W_out block)
-struct Bars {
-  uint32_t base;
-  __device__ uint32_t full(int s) const { return base + 8u * s; }
-  __device__ uint32_t empty(int s) const { return base + 8u * (NSTAGE_MAX + s); }
-  __device__ uint32_t acc() const { return base + 8u * (2 * NSTAGE_MAX); }          // layer accumulated (multicast commit)
-  __device__ uint32_t aready() const { return base + 8u * (2 * NSTAGE_MAX + 1); }   // leader only: both A images ready
-  __device__ uint32_t tmem_slot() const { return base + 8u * (2 * NSTAGE_MAX + 2); }
-};
-constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE_MAX + 2);
-
-// ---- forward kernel (v2, overlapped): shared-memory layout and barrier block
+// ---- layer-chain kernels (forward, dgrad chain): shared-memory layout and barrier block
 //   [A image 128 KB][weight ring 5 x 16 KB][bias: 2 layers x 2 KB][W_out 4 KB][row partial sums 1 KB][barriers]
 namespace fw {
 constexpr int NSTAGE = 5;
@@ -97,7 +69,7 @@ constexpr int OFF_WOUT = OFF_BIAS + 2 * BIAS_BYTES;
 constexpr int OFF_OSUM = OFF_WOUT + WOUT_BYTES;
 constexpr int OFF_BAR = OFF_OSUM + TILE_M * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(SMEM_BYTES <= 232448, "forward kernel exceeds the 227 KB shared-memory window");
+static_assert(SMEM_BYTES <= 232448, "layer-chain kernels exceed the 227 KB shared-memory window");
 //   full[s] / empty[s] : weight ring, as in Bars
 //   acc[h]             : temporal N-half h (output columns [256h, 256h+256)) of the current layer accumulated
 //                        (multicast tcgen05.commit -> both CTAs)

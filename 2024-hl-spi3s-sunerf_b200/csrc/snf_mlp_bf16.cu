@@ -2,18 +2,22 @@
 // ONE persistent, warp-specialised kernel per pass.  Replaces PositionalEncoding.forward / NeRF.forward /
 // NeRF_DT.forward (sunerf/model/model.py:123-132, 44-57, 169-187) in "bf16-MLP mode" (BASELINE.json: 1e-2).
 //
-// Per CTA: one tile of 128 points at a time; the activations never leave the SM between layers:
-//   warp 0      TMA producer : streams the pre-packed bf16 weights (UMMA K-major SWIZZLE_128B image) from L2 with
-//                              32 KB cp.async.bulk copies through a 3-stage mbarrier ring; the fp32 W_out rows ride
-//                              through the same ring as a 4 KB pseudo-block at the end of each tile
-//   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=256, K=16) per k-step; A = activations in
-//                              shared memory (128 KB, same swizzled image), D = 128x512 fp32 in TMEM (all 512 cols)
-//   warps 2-9   epilogue     : thread = (row, column half).  Double-buffered tcgen05.ld of the accumulator, + bias
-//                              (staged in shared memory once per layer), sin, bf16, st.shared back into the A image
-//                              for the next layer; layer 0's A image is the sin/cos encoding computed in place;
-//                              the 512->2 output layer is a register dot product fused into the last epilogue
-// Training mode additionally writes, per layer, the activation image h = sin(pre) (TMA bulk store straight from the
-// A image) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
+// One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 points, 384 threads per CTA; the activations
+// never leave the SM between layers:
+//   warp 0      TMA producer : streams this CTA's half (128 output features, 16 KB) of every pre-packed bf16 weight
+//                              block (UMMA K-major SWIZZLE_128B image, L2 evict_last) through a 5-stage mbarrier ring
+//   warp 1      MMA issuer   : leader CTA: tcgen05.mma M=256 (pair) x N=256 x K=16, A = activation image in shared
+//                              memory (128 KB), D = 128 x 512 fp32 = all of TMEM; peer CTA: relays "my half of the
+//                              stage has landed" to the leader with a relaxed remote mbarrier arrive
+//   warps 4-11  epilogue     : thread = (row, 32-column group).  A layer is accumulated as two temporal N-halves; the
+//                              epilogue of half 0 (TMEM -> +bias -> sin -> bf16) runs under the MMAs of half 1 and
+//                              keeps its result in registers until the A image may be overwritten, half 1 is written
+//                              slab by slab so the next layer's MMAs start k-slab by k-slab.
+//                              Layer 0's A image is the sin/cos encoding computed in place; the 512->2 output layer
+//                              is a register dot product fused into the last epilogue.
+//   setmaxnreg  40 registers for the control warpgroup, 232 for the two epilogue warpgroups.
+// Training mode additionally writes, per layer, the activation image h = sin(pre) (TMA bulk stores straight from the
+// A image, 4 KB per warp pair) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
 #include "snf_bf16_common.cuh"
 
 namespace snf {
@@ -199,7 +203,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               tcgen05_fence_after();
               if (elect_one()) {
                 const uint64_t ad = adesc0 + (uint64_t)((ks * SLAB_BYTES) >> 4), bd = bdesc0 + (uint64_t)((s * WHALF_BYTES) >> 4);
-#ifndef SNF_EXP_NO_MMA
                 if (l == 0 && ks == 1) {
 #pragma unroll
                   for (int k4 = 0; k4 < (K0 - 64) / 16; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, 1);
@@ -207,7 +210,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (ks | k4) != 0);
                 }
-#endif
                 mma_commit_2cta(bar.empty(s), 3);         // frees the stage in both CTAs
                 if (ks == nslab - 1) mma_commit_2cta(bar.acc(h), 3);   // this half of the layer is accumulated, in both CTAs
               }
@@ -392,11 +394,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               const float4 b = *reinterpret_cast<const float4 *>(bl + col0 + i);
               const float v0 = __uint_as_float(cur[i]) + b.x, v1 = __uint_as_float(cur[i + 1]) + b.y;
               const float v2 = __uint_as_float(cur[i + 2]) + b.z, v3 = __uint_as_float(cur[i + 3]) + b.w;
-#ifdef SNF_EXP_NO_SIN
-              const float s0 = v0, s1 = v1, s2 = v2, s3 = v3;
-#else
               const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
-#endif
               pk[i / 2] = pack_bf16x2(s0, s1); pk[i / 2 + 1] = pack_bf16x2(s2, s3);
               if (TRAIN) cq[i / 4] = cosq_pack4(cosq_enc(v0), cosq_enc(v1), cosq_enc(v2), cosq_enc(v3));   // cos(pre) for the backward
               if (last) {   // fused output layer: out = W_out h + b_out
