@@ -6,7 +6,7 @@
 //     l = 7..1:  dpre_{l-1} = (dpre_l W_l) * C_{l-1}  -- tcgen05.mma with A = dpre_l image in shared memory, B = W_l^T
 //     blocks streamed by TMA, D in TMEM; every dpre_l image is bulk-stored to HBM (D_l) for the weight gradients.
 //  wgrad        (mlp_wgrad_bf16_kernel): dW_l[o,i] = sum_p D_l[p,o] Hprev_l[p,i].  The saved images are read
-//     "transposed" as MN-major UMMA operands (same bytes, different descriptor), 32 points per pipeline stage;
+//     "transposed" as MN-major UMMA operands (same bytes, different descriptor), 64 points per pipeline stage;
 //     a CTA owns a 128(o) x 512(i) fp32 accumulator (all of TMEM) for a range of tiles, then flushes it with
 //     red.global.add.v4.f32 into the flat gradient buffer.  The otherwise idle epilogue warps sum the D_l stages
 //     over points for the bias gradients.
@@ -313,11 +313,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
 // CTA pairs (tcgen05 cta_group::2, M = 256 output features across the pair, N = 256 input features per instruction):
 // CTA r of a pair owns output features [256 ob + 128 r, +128) - its A operand (2 slabs of D_l) and its 128 x 512 fp32
 // accumulator (all of its TMEM) - and supplies half of every B operand (2 of the 4 H slabs of each N = 256
-// instruction), so a pipeline stage of 32 points is 24 KB per CTA instead of the 40 KB a single-CTA tile needs.
-constexpr int WG_KSTAGE = 32;                           // points per pipeline stage
-constexpr int WG_SLAB_STAGE = WG_KSTAGE * 128;          // 4 KB: 32 rows of one 64-feature slab
-constexpr int WG_STAGE_BYTES = 6 * WG_SLAB_STAGE;       // 2 (own o) + 2 x 2 (own half of i, two N-halves) slabs = 24 KB
-constexpr int WG_NSTAGE = 9;
+// instruction), so a pipeline stage of 64 points is 48 KB per CTA instead of the 80 KB a single-CTA tile needs.
+constexpr int WG_KSTAGE = 64;                           // points per pipeline stage
+constexpr int WG_SLAB_STAGE = WG_KSTAGE * 128;          // 8 KB: 64 rows of one 64-feature slab
+constexpr int WG_STAGE_BYTES = 6 * WG_SLAB_STAGE;       // 2 (own o) + 2 x 2 (own half of i, two N-halves) slabs = 48 KB
+constexpr int WG_NSTAGE = 4;   // few large copies: a single producer thread sustains only ~1 bulk copy per 100-300 cycles
 constexpr int WG_SMEM_BYTES = WG_NSTAGE * WG_STAGE_BYTES + 256;
 static_assert(WG_SMEM_BYTES <= 232448, "wgrad ring exceeds shared memory");
 
@@ -456,7 +456,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
       int l, ob, t0, t1; decode(item, l, ob, t0, t1);
       const int o = ob * 256 + (int)rank * 128 + row;
       float bsum = 0.f;
-      // column `row` of the D stage: slab row>>6, element row&63 of each of the 32 point-lines
+      // column `row` of the D stage: slab row>>6, element row&63 of each of the 64 point-lines
       const int bslab = row >> 6, bc8 = (row & 63) >> 3, be = row & 7;
       for (int t = t0; t < t1; ++t)
         for (int qd = 0; qd < TILE_M / WG_KSTAGE; ++qd) {
