@@ -14,17 +14,22 @@ constexpr int K0 = 96;                       // layer-0 K: 84 features + 4 bf16 
 constexpr int SLAB_BYTES = TILE_M * 128;     // one K-slab (64 bf16) of a 128-row image: 16 KB
 constexpr int A_BYTES = 8 * SLAB_BYTES;      // 128 KB activation image
 constexpr int C_BYTES = TILE_M * D;          // 64 KB: cos(pre) of one tile and layer as int8 (x 127), chunk-major:
-                                             // [slab (8)][ch (2)][k (2)][row (128)] x 16 B; a warp access covers 512 B
+                                             // [slab (8)][16-column chunk (4)][row (128)] x 16 B; a warp access covers 512 B
 
 // ---- layer-chain kernels (forward, dgrad): CTA pairs, tcgen05 cta_group::2, M=256 N=256 K=16
 constexpr int NCHUNK = 256;                  // output features per MMA / per weight block
 constexpr int WBLK_BYTES = NCHUNK * 128;     // weight block: 256 output features x 64 k = 32 KB
 constexpr int WHALF_BYTES = WBLK_BYTES / 2;  // each CTA of the pair streams half of every block: 16 KB
-constexpr int N_EPI_WARPS = 8;
-constexpr int N_EPI = N_EPI_WARPS * 32;      // 256 epilogue threads: (row, column half)
+constexpr int EPI_GROUPS = 2;                // epilogue warps per TMEM lane quarter: each owns 64 / EPI_GROUPS columns of a step
+constexpr int CPT = 64 / EPI_GROUPS;         // accumulator columns per thread and step (a step = one 64-column k-slab)
+constexpr int CHUNKS = CPT / 8;              // 16-byte chunks of the A image per thread and step
+constexpr int N_EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int N_EPI = N_EPI_WARPS * 32;      // epilogue threads: (row, column group)
+constexpr int QUAD_THREADS = 32 * EPI_GROUPS;   // the warps of one TMEM lane quarter (named barrier 2 + q): they own 32 rows
 constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2-3 idle;
-constexpr int NTHREADS = 128 + N_EPI;        // warpgroups 1-2 (warps 4..11): epilogue.  Registers are re-balanced with setmaxnreg:
-constexpr int REGS_CTRL = 40, REGS_EPI = 232;   // per SM sub-partition 1 control warp + 2 epilogue warps: 40 + 2 x 232 <= 512
+constexpr int NTHREADS = 128 + N_EPI;        // the following warpgroups: epilogue.  Registers are re-balanced with setmaxnreg:
+constexpr int REGS_CTRL = 40, REGS_EPI = EPI_GROUPS == 2 ? 232 : 112;   // per SM sub-partition: 40 + EPI_GROUPS x REGS_EPI <= 512
+static_assert(EPI_GROUPS == 2 || EPI_GROUPS == 4, "CPT must be 32 or 16 (tcgen05.ld x32 / x16)");
 constexpr int BIAS_BYTES = D * 4;
 
 constexpr int FWD_BLOCKS = 2 * 2 + 7 * 16;   // forward weight blocks: layer 0 (2 n-halves x 2 k-slabs) + 7 x (2 x 8)
@@ -67,7 +72,7 @@ constexpr int OFF_RING = A_BYTES;
 constexpr int OFF_BIAS = OFF_RING + NSTAGE * WHALF_BYTES;
 constexpr int OFF_WOUT = OFF_BIAS + 2 * BIAS_BYTES;
 constexpr int OFF_OSUM = OFF_WOUT + WOUT_BYTES;
-constexpr int OFF_BAR = OFF_OSUM + TILE_M * 8;
+constexpr int OFF_BAR = OFF_OSUM + (EPI_GROUPS - 1) * TILE_M * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "layer-chain kernels exceed the 227 KB shared-memory window");
 //   full[s] / empty[s] : weight ring, as in Bars

@@ -239,24 +239,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
   }
   } else {
     reg_alloc<REGS_EPI>();
-    // =========================== epilogue warps: 256 threads.  Thread = (row, ch): in temporal half h, step j it owns
-    // the 32 accumulator columns 256h + 64j + 32ch .. +31, i.e. chunks 4ch..4ch+3 of A slab 4h + j.
+    // =========================== epilogue warps.  Thread = (row, g): in temporal half h, step j it owns the CPT
+    // accumulator columns 256h + 64j + CPT g .. , i.e. chunks CHUNKS g .. of A slab 4h + j.
     const int e = warp - EPI_WARP0;
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int ch = e >> 2;
+    const int g = e >> 2;                             // column group inside a step (0 .. EPI_GROUPS-1)
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - EPI_WARP0 * 32;                  // 0..255
-    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
+    const int et = threadIdx.x - EPI_WARP0 * 32;      // 0 .. N_EPI-1
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + g * CPT;
     uint32_t ready_addr[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) ready_addr[k] = rank == 0 ? bar.ready(k) : mapa_shared(bar.ready(k), 0);
-    // one arrival per warp: every lane has fenced its own writes, __syncwarp orders them before lane 0's release
 #ifdef SNF_PROF
     int estamp = 0; bool etrace = false;
 #define ESTAMP() do { if (etrace && e == 0 && lane == 0 && estamp < 512) g_trace[3][estamp++] = clock64(); } while (0)
 #else
 #define ESTAMP()
 #endif
+    // one arrival per warp: every lane has fenced its own writes, __syncwarp orders them before lane 0's arrival
     auto arrive_ready = [&](int k) {
       __syncwarp();
       ESTAMP();
@@ -266,8 +266,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    uint32_t ph = 0;
+    // the quarter's 32 rows of slabs [sl0, sl0+nsl) are complete in the A image: one elected lane TMA-stores them
     const uint64_t stream_pol = l2_policy_evict_first();   // saved activations: written once, read by the backward much later
+    auto store_quarter = [&](uint8_t *img, int sl0, int nsl) {
+      named_bar_sync(2 + q, QUAD_THREADS);
+      if (g == 0 && lane == 0) {
+        for (int sl = sl0; sl < sl0 + nsl; ++sl)
+          bulk_s2g_hint(img + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
+        bulk_commit();
+      }
+    };
+    auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
+      if (g == 0 && lane == 0) bulk_wait_read_all();
+      named_bar_sync(2 + q, QUAD_THREADS);
+    };
+    uint32_t ph = 0;
     PROF_DECL(t_acc0); PROF_DECL(t_acc1); PROF_DECL(t_enc); PROF_T0(t_begin);
     tcgen05_fence_before();
     arrive_ready(4);                                  // D half 1 is free for the first tile
@@ -278,56 +291,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
       etrace = TRAIN == SNF_TRACE_TRAIN && blockIdx.x == 0 && tp == pair + npairs;
 #endif
       // ---- layer-0 operand: positional encoding of this row, written straight into the A image (slabs 0, 1).
-      //      ch 0: x and frequencies 0..4 ; ch 1: bf16 residual of x, zero padding and frequencies 5..9
+      //      The 10 frequencies are dealt round-robin to the column groups; group 0 adds the raw coordinates, the last
+      //      group the bf16 residual of x and the zero padding.
       {
         PROF_T0(t0);
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M) xv = p.x[m];
         const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
-        if (TRAIN) {   // the pair's bulk stores of the previous tile's last layer must have left the A image
-          if (ch == 0 && lane == 0) bulk_wait_read_all();
-          named_bar_sync(2 + q, 64);
-        }
+        if (TRAIN) wait_quarter_stores();             // the previous tile's last layer must have left the A image
         auto put8 = [&](int feat0, float a, float b, float c, float d) {   // 4 consecutive features (8 bytes)
           const int c8 = feat0 >> 3;
           *reinterpret_cast<uint2 *>(gA + (c8 >> 3) * SLAB_BYTES + sw128_chunk_off(row, c8 & 7) + (feat0 & 7) * 2) =
               make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
         };
-        if (ch == 0) {
-          put8(0, xc[0], xc[1], xc[2], xc[3]);
-        } else {
+        if (g == 0) put8(0, xc[0], xc[1], xc[2], xc[3]);
+        if (g == EPI_GROUPS - 1) {
           float rs[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) rs[c] = xc[c] - __bfloat162float(__float2bfloat16_rn(xc[c]));   // what bf16 drops from x
           put8(84, rs[0], rs[1], rs[2], rs[3]);
           put8(88, 0.f, 0.f, 0.f, 0.f);
           put8(92, 0.f, 0.f, 0.f, 0.f);
-          if (TRAIN)   // features 96..127 of the saved encoder image (read by the layer-0 wgrad, never by the forward MMAs)
-            for (int c8 = 4; c8 < 8; ++c8)
-              *reinterpret_cast<uint4 *>(gA + SLAB_BYTES + sw128_chunk_off(row, c8)) = make_uint4(0, 0, 0, 0);
         }
+        if (TRAIN && g == EPI_GROUPS - 2)   // features 96..127 of the saved encoder image (read by the layer-0 wgrad only)
+          for (int c8 = 4; c8 < 8; ++c8)
+            *reinterpret_cast<uint4 *>(gA + SLAB_BYTES + sw128_chunk_off(row, c8)) = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int fi = 0; fi < 5; ++fi) {
-          const int f = ch * 5 + fi;
-          float sv[4], cv[4];
+        for (int fi = 0; fi < (10 + EPI_GROUPS - 1) / EPI_GROUPS; ++fi) {
+          const int f = fi * EPI_GROUPS + g;
+          if (f < 10) {
+            float sv[4], cv[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) sincosf(xc[c] * (float)(1 << f) * 0.5f, &sv[c], &cv[c]);   // exact scalings
-          put8(4 + f * 4, sv[0], sv[1], sv[2], sv[3]);
-          put8(44 + f * 4, cv[0], cv[1], cv[2], cv[3]);
+            for (int c = 0; c < 4; ++c) sincosf(xc[c] * (float)(1 << f) * 0.5f, &sv[c], &cv[c]);   // exact scalings
+            put8(4 + f * 4, sv[0], sv[1], sv[2], sv[3]);
+            put8(44 + f * 4, cv[0], cv[1], cv[2], cv[3]);
+          }
         }
-        if (TRAIN) {   // this pair's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
-          fence_proxy_async_smem();
-          named_bar_sync(2 + q, 64);
-          if (ch == 0 && lane == 0) {
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        arrive_ready(0);
+        if (TRAIN) {   // the quarter's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
+          named_bar_sync(2 + q, QUAD_THREADS);
+          if (g == 0 && lane == 0) {
             uint8_t *esave = p.save_enc + (int64_t)tile * 2 * SLAB_BYTES + q * PAIR_BYTES;
             bulk_s2g_hint(esave, sA + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
             bulk_s2g_hint(esave + SLAB_BYTES, sA + SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
             bulk_commit();
           }
         }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        arrive_ready(0);
         PROF_ADD(t_enc, t0);
       }
       // ---- layers
@@ -337,7 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         const float *bl = bias_s + (l & 1) * D;
         uint8_t *hsave = TRAIN ? p.save_h + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
         uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * C_BYTES : nullptr;
-        uint32_t held[64];                            // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
+        uint32_t held[4 * CPT / 2];                   // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -348,49 +359,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
           }
           ESTAMP();
           tcgen05_fence_after();
-          uint32_t accA[32], accB[32];
-          tmem_ld32(tm_row + h * 256, accA);
+          uint32_t accA[CPT], accB[CPT];
+          tmem_ld(tm_row + h * 256, accA);
           if (h == 0) {
             // every warp is past the previous layer: the other bias buffer is idle -> stage the next layer's bias
             const int ln = (l + 1) & (NH - 1);
-            reinterpret_cast<float2 *>(bias_s + (ln & 1) * D)[et] = __ldg(reinterpret_cast<const float2 *>(bias_all + ln * D) + et);
+            for (int i = et; i < D; i += N_EPI) bias_s[(ln & 1) * D + i] = __ldg(bias_all + ln * D + i);
           } else if (!last || TRAIN) {
             // all MMAs of layer l are complete: the A image may be overwritten with h_l, half 0 first (from registers)
-            if (TRAIN) {   // ... once the pair's bulk stores of h_{l-1} (or of the encoder image) have read it
-              if (ch == 0 && lane == 0) bulk_wait_read_all();
-              named_bar_sync(2 + q, 64);
-            }
+            if (TRAIN) wait_quarter_stores();         // ... once the stores of h_{l-1} (or of the encoder image) have read it
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
-                    make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
+              for (int c = 0; c < CHUNKS; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
+                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
+                               held[(CPT / 2) * j + 4 * c + 3]);
             fence_proxy_async_smem();
             if (!last) {   // hand the slabs to the MMA issuer first: the stores below are off the critical path
               tcgen05_fence_before();
               arrive_ready(0);
             }
-            if (TRAIN) {
-              named_bar_sync(2 + q, 64);
-              if (ch == 0 && lane == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bulk_s2g_hint(hsave + j * SLAB_BYTES + q * PAIR_BYTES, sA + j * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-                bulk_commit();
-              }
-            }
+            if (TRAIN) store_quarter(hsave, 0, 4);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t(&cur)[32] = (j & 1) ? accB : accA;
-            uint32_t(&nxt)[32] = (j & 1) ? accA : accB;
+            uint32_t(&cur)[CPT] = (j & 1) ? accB : accA;
+            uint32_t(&nxt)[CPT] = (j & 1) ? accA : accB;
             tmem_ld_wait(cur);
-            if (j + 1 < 4) tmem_ld32(tm_row + h * 256 + (j + 1) * 64, nxt);
-            const int col0 = h * 256 + j * 64 + ch * 32;
+            if (j + 1 < 4) tmem_ld(tm_row + h * 256 + (j + 1) * 64, nxt);
+            const int col0 = h * 256 + j * 64 + g * CPT;
             const int sl = h * 4 + j;
-            uint32_t pk[16], cq[8];
+            uint32_t pk[CPT / 2], cq[CPT / 4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < CPT; i += 4) {
               const float4 b = *reinterpret_cast<const float4 *>(bl + col0 + i);
               const float v0 = __uint_as_float(cur[i]) + b.x, v1 = __uint_as_float(cur[i + 1]) + b.y;
               const float v2 = __uint_as_float(cur[i + 2]) + b.z, v3 = __uint_as_float(cur[i + 3]) + b.w;
@@ -404,32 +406,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 o1 += s0 * wb.x + s1 * wb.y + s2 * wb.z + s3 * wb.w;
               }
             }
-            if (TRAIN) {   // cos(pre) for the dgrad chain: 2 x 16 B per thread, a warp store covers 512 contiguous bytes
+            if (TRAIN) {   // cos(pre) for the dgrad chain: CPT bytes per thread, a warp store covers 512 contiguous bytes
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                st_stream16(psave + ((((sl * 2 + ch) * 2 + k) * TILE_M + row) << 4), cq[4 * k], cq[4 * k + 1], cq[4 * k + 2], cq[4 * k + 3]);
+              for (int k = 0; k < CPT / 16; ++k)
+                st_stream16(psave + (((sl * 4 + g * (CPT / 16) + k) * TILE_M + row) << 4), cq[4 * k], cq[4 * k + 1], cq[4 * k + 2], cq[4 * k + 3]);
             }
             if (!last || TRAIN) {
               if (h == 0) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) held[16 * j + k] = pk[k];
+                for (int k = 0; k < CPT / 2; ++k) held[(CPT / 2) * j + k] = pk[k];
               } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+                for (int c = 0; c < CHUNKS; ++c)
+                  *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
                       make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 fence_proxy_async_smem();
                 if (!last) {
                   tcgen05_fence_before();
                   arrive_ready(1 + j);
                 }
-                if (TRAIN) {   // h_l for the weight gradients: the pair's 32 rows of this slab are one contiguous 4 KB block
-                  named_bar_sync(2 + q, 64);
-                  if (ch == 0 && lane == 0) {
-                    bulk_s2g_hint(hsave + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-                    bulk_commit();
-                  }
-                }
+                if (TRAIN) store_quarter(hsave, sl, 1);   // h_l for the weight gradients
               }
             }
           }
@@ -438,17 +434,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         if (last) {
           tcgen05_fence_before();
           arrive_ready(4);                            // D half 1 drained: the next tile's layer 0 may use it
-          // combine the two column groups of each row
-          if (ch == 1) osum_s[row] = make_float2(o0, o1);
+          // combine the column groups of each row
+          if (g > 0) osum_s[(g - 1) * TILE_M + row] = make_float2(o0, o1);
           named_bar_sync(1, N_EPI);
-          if (ch == 0 && m < p.M) {
-            const float2 o = osum_s[row];
-            p.out[m] = make_float2((o0 + o.x) + __ldg(b_out) + p.off0, (o1 + o.y) + __ldg(b_out + 1) + p.off1);
+          if (g == 0 && m < p.M) {
+#pragma unroll
+            for (int gg = 1; gg < EPI_GROUPS; ++gg) { const float2 o = osum_s[(gg - 1) * TILE_M + row]; o0 += o.x; o1 += o.y; }
+            p.out[m] = make_float2(o0 + __ldg(b_out) + p.off0, o1 + __ldg(b_out + 1) + p.off1);
           }
         }
       }
     }
-    if (TRAIN && ch == 0 && lane == 0) bulk_wait_all();
+    if (TRAIN && g == 0 && lane == 0) bulk_wait_all();
 #ifdef SNF_PROF
     if (e == 0 && lane == 0) {
       g_prof[TRAIN][blockIdx.x * 8 + 3] = clock64() - t_begin;

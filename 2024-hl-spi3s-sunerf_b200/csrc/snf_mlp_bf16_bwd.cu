@@ -163,9 +163,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
   }
   } else {
     reg_alloc<REGS_EPI>();
-    // =========================== epilogue warps: thread = (row, ch); step (h, j) <-> slab 4h + j, chunks 4ch..4ch+3
-    const int e = warp - EPI_WARP0, q = warp & 3, ch = e >> 2, row = q * 32 + lane;
-    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
+    // =========================== epilogue warps: thread = (row, g); step (h, j) <-> slab 4h + j, chunks CHUNKS g ..
+    const int e = warp - EPI_WARP0, q = warp & 3, g = e >> 2, row = q * 32 + lane;
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + g * CPT;
     uint32_t ready_addr[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) ready_addr[k] = rank == 0 ? bar.ready(k) : mapa_shared(bar.ready(k), 0);
@@ -176,33 +176,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // this thread's 32 cosines of one step: 2 x 16 int8, offset-binary after the XOR (cosq_get)
-    auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[2]) {
+    // this thread's CPT cosines of one step: CPT / 16 x 16 int8, offset-binary after the XOR (cosq_get)
+    constexpr int NQ = CPT / 16;
+    auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[NQ]) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        uint4 v = __ldcs(reinterpret_cast<const uint4 *>(img + ((((sl * 2 + ch) * 2 + k) * TILE_M + row) << 4)));
+      for (int k = 0; k < NQ; ++k) {
+        uint4 v = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 4 + g * NQ + k) * TILE_M + row) << 4)));
         v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
         pv[k] = v;
       }
     };
-    auto cos_of = [&](const uint4 (&pv)[2], int i) {   // element i (0..31) of the step
+    auto cos_of = [&](const uint4 (&pv)[NQ], int i) {   // element i (0 .. CPT-1) of the step
       const uint4 &v = pv[i >> 4];
       const int wi = (i >> 2) & 3;
       const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
       return cosq_get(w, i & 3);
     };
-    // slab sl of the A image is complete for this pair's 32 rows: hand it to the MMAs and store it for the wgrad
-    const uint64_t stream_pol = l2_policy_evict_first();
     // hand complete slabs to the MMA issuer first (ready barrier k, or none), then store them for the wgrad
+    const uint64_t stream_pol = l2_policy_evict_first();
     auto publish = [&](uint8_t *dimg, int sl0, int nsl, int k) {
       fence_proxy_async_smem();
       if (k >= 0) { tcgen05_fence_before(); arrive_ready(k); }
-      named_bar_sync(2 + q, 64);
-      if (ch == 0 && lane == 0) {
+      named_bar_sync(2 + q, QUAD_THREADS);
+      if (g == 0 && lane == 0) {
         for (int sl = sl0; sl < sl0 + nsl; ++sl)
           bulk_s2g_hint(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
         bulk_commit();
       }
+    };
+    auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
+      if (g == 0 && lane == 0) bulk_wait_read_all();
+      named_bar_sync(2 + q, QUAD_THREADS);
     };
     uint32_t ph = 0;
     for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
@@ -210,7 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       const int64_t m = (int64_t)tile * TILE_M + row;
       const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * C_BYTES;
       uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
-      uint4 pn[2];
+      uint4 pn[NQ];
       // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7), written straight into the A image
       {
         const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * C_BYTES;
@@ -218,17 +222,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         load_pre(p7, 0, pn);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
-        if (ch == 0 && lane == 0) bulk_wait_read_all();   // the previous tile's last stores have left the A image
-        named_bar_sync(2 + q, 64);
+        wait_quarter_stores();                        // the previous tile's last stores have left the A image
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
-          uint4 pv[2];
-          pv[0] = pn[0]; pv[1] = pn[1];
+          uint4 pv[NQ];
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) pv[k] = pn[k];
           if (sl + 1 < 8) load_pre(p7, sl + 1, pn);
           else load_pre(pre_tile + (int64_t)(NH - 2) * C_BYTES, 0, pn);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = sl * 64 + (4 * ch + c) * 8;
+          for (int c = 0; c < CHUNKS; ++c) {
+            const int col = sl * 64 + (CHUNKS * g + c) * 8;
             const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col), wa1 = *reinterpret_cast<const float4 *>(wout_s + col + 4);
             const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col + 4);
             uint4 o;
@@ -236,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * cos_of(pv, 8 * c + 2), (gg.x * wa0.w + gg.y * wb0.w) * cos_of(pv, 8 * c + 3));
             o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * cos_of(pv, 8 * c + 4), (gg.x * wa1.y + gg.y * wb1.y) * cos_of(pv, 8 * c + 5));
             o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * cos_of(pv, 8 * c + 6), (gg.x * wa1.w + gg.y * wb1.w) * cos_of(pv, 8 * c + 7));
-            *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) = o;
+            *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) = o;
           }
           publish(d7, sl, 1, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
         }
@@ -248,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * C_BYTES;
         const uint8_t *pnext = pre_tile + (int64_t)(l >= 2 ? l - 2 : 0) * C_BYTES;
         uint8_t *dprev = d_tile + (int64_t)(l - 1) * A_BYTES;
-        uint32_t held[64];
+        uint32_t held[4 * CPT / 2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(bar.acc(h), ph);
@@ -257,43 +261,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           tmem_ld16(tm_row + h * 256, accA);
           if (h == 1) {
             // all MMAs of layer l are complete: the A image may be overwritten with dpre_{l-1}, half 0 from registers
-            if (ch == 0 && lane == 0) bulk_wait_read_all();   // ... once the stores of dpre_l have read it
-            named_bar_sync(2 + q, 64);
+            wait_quarter_stores();                    // ... once the stores of dpre_l have read it
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
-                    make_uint4(held[16 * j + 4 * c], held[16 * j + 4 * c + 1], held[16 * j + 4 * c + 2], held[16 * j + 4 * c + 3]);
+              for (int c = 0; c < CHUNKS; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
+                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
+                               held[(CPT / 2) * j + 4 * c + 3]);
             publish(dprev, 0, 4, last ? -1 : 0);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int sl = h * 4 + j;
-            uint4 pv[2];
-            pv[0] = pn[0]; pv[1] = pn[1];
+            uint4 pv[NQ];
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) pv[k] = pn[k];
             if (sl + 1 < 8) load_pre(pprev, sl + 1, pn);
             else if (!last) load_pre(pnext, 0, pn);
-            uint32_t pk[16];
-            auto half_step = [&](const uint32_t (&a)[16], int c0) {   // 16 columns = chunks c0, c0 + 1 of this step
+            uint32_t pk[CPT / 2];
+            auto part16 = [&](const uint32_t (&a)[16], int c0) {   // 16 columns = chunks c0, c0 + 1 of this step
 #pragma unroll
               for (int i = 0; i < 16; i += 2)
                 pk[4 * c0 + i / 2] = pack_bf16x2(__uint_as_float(a[i]) * cos_of(pv, 8 * c0 + i),
                                                  __uint_as_float(a[i + 1]) * cos_of(pv, 8 * c0 + i + 1));
             };
-            tmem_ld_wait(accA);
-            tmem_ld16(tm_row + h * 256 + j * 64 + 16, accB);
-            half_step(accA, 0);
-            tmem_ld_wait(accB);
-            if (j + 1 < 4) tmem_ld16(tm_row + h * 256 + (j + 1) * 64, accA);
-            half_step(accB, 2);
+            if (CPT == 32) {
+              tmem_ld_wait(accA);
+              tmem_ld16(tm_row + h * 256 + j * 64 + 16, accB);
+              part16(accA, 0);
+              tmem_ld_wait(accB);
+              if (j + 1 < 4) tmem_ld16(tm_row + h * 256 + (j + 1) * 64, accA);
+              part16(accB, 2);
+            } else {                                  // CPT == 16: one load per step, the next step's in flight
+              uint32_t(&cur)[16] = (j & 1) ? accB : accA;
+              uint32_t(&nxt)[16] = (j & 1) ? accA : accB;
+              tmem_ld_wait(cur);
+              if (j + 1 < 4) tmem_ld16(tm_row + h * 256 + (j + 1) * 64, nxt);
+              part16(cur, 0);
+            }
             if (h == 0) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) held[16 * j + k] = pk[k];
+              for (int k = 0; k < CPT / 2; ++k) held[(CPT / 2) * j + k] = pk[k];
             } else {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, 4 * ch + c)) =
+              for (int c = 0; c < CHUNKS; ++c)
+                *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
               publish(dprev, sl, 1, last ? -1 : 1 + j);
             }
@@ -302,7 +315,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         ph ^= 1;
       }
     }
-    if (ch == 0 && lane == 0) bulk_wait_all();
+    if (g == 0 && lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   cluster_sync_all();
