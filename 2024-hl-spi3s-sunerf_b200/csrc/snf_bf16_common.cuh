@@ -20,7 +20,10 @@ constexpr int C_BYTES = TILE_M * D;          // 64 KB: cos(pre) of one tile and 
 constexpr int NCHUNK = 256;                  // output features per MMA / per weight block
 constexpr int WBLK_BYTES = NCHUNK * 128;     // weight block: 256 output features x 64 k = 32 KB
 constexpr int WHALF_BYTES = WBLK_BYTES / 2;  // each CTA of the pair streams half of every block: 16 KB
-constexpr int EPI_GROUPS = 2;                // epilogue warps per TMEM lane quarter: each owns 64 / EPI_GROUPS columns of a step
+#ifndef SNF_EPI_GROUPS
+#define SNF_EPI_GROUPS 2                     // per translation unit: the forward uses 4 (16 epilogue warps), the dgrad chain 2
+#endif
+constexpr int EPI_GROUPS = SNF_EPI_GROUPS;   // epilogue warps per TMEM lane quarter: each owns 64 / EPI_GROUPS columns of a step
 constexpr int CPT = 64 / EPI_GROUPS;         // accumulator columns per thread and step (a step = one 64-column k-slab)
 constexpr int CHUNKS = CPT / 8;              // 16-byte chunks of the A image per thread and step
 constexpr int N_EPI_WARPS = 4 * EPI_GROUPS;
@@ -28,7 +31,7 @@ constexpr int N_EPI = N_EPI_WARPS * 32;      // epilogue threads: (row, column g
 constexpr int QUAD_THREADS = 32 * EPI_GROUPS;   // the warps of one TMEM lane quarter (named barrier 2 + q): they own 32 rows
 constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2-3 idle;
 constexpr int NTHREADS = 128 + N_EPI;        // the following warpgroups: epilogue.  Registers are re-balanced with setmaxnreg:
-constexpr int REGS_CTRL = 40, REGS_EPI = EPI_GROUPS == 2 ? 232 : 112;   // per SM sub-partition: 40 + EPI_GROUPS x REGS_EPI <= 512
+constexpr int REGS_CTRL = 40, REGS_EPI = EPI_GROUPS == 2 ? 232 : 104;   // 128 x CTRL + N_EPI x EPI must fit the launch allocation (NTHREADS x 168 or 96)
 static_assert(EPI_GROUPS == 2 || EPI_GROUPS == 4, "CPT must be 32 or 16 (tcgen05.ld x32 / x16)");
 constexpr int BIAS_BYTES = D * 4;
 

@@ -43,12 +43,13 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; started before the warm-up (nvidia-smi takes a moment
+    to come up), only the samples that fall inside the timed window [mark_start, mark_end] are reported."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
@@ -60,17 +61,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.25)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.time()) + 0.15
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 6]
+        if not rows:                       # window shorter than the sampling period: take the nearest samples
+            rows = [r for ts, r in self.rows if len(r) >= 6][-3:]
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
                 'samples': len(sm)}
 
@@ -222,12 +233,13 @@ def main():
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(args.warmup):
-        step_resident()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step_resident()
     mlp_events.clear()
+    clocks.mark_start()
     l0 = ops.launch_count()
     ms = timed_loop(step_resident, args.steps)
     launches = ops.launch_count() - l0
@@ -238,6 +250,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed_loop(step_e2e, args.steps)
+    clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
     trainer.check_finite()
 
