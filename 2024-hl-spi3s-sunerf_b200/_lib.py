@@ -89,6 +89,8 @@ _PROTOS = {
     'snf_composite_dt_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     'snf_render_epilogue': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _P, _F, _P, _P]),
     'snf_train_loss': (_I, [_P, _P, _P, _P, _L, _I, _L, _I, _F, _F, _F, _P, _P, _P, _P, _P]),
+    'snf_debug_time_backward': (_I, [_I]),
+    'snf_debug_backward_ms': (_I, [_P]),
     'snf_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _F, _P, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS)

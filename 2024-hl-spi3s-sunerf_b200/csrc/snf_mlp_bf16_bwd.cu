@@ -581,6 +581,36 @@ int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
   return launch_status();
 }
 
+// Per-kernel CUDA-event timing of the backward (bench.py's roofline break-down): off by default; when armed, every call
+// records into its own event set (no host sync on the hot path), the sums are formed when the getter is called.
+constexpr int BWD_EV_SETS = 256;
+static bool g_time_bwd = false;
+static cudaEvent_t g_bwd_ev[BWD_EV_SETS][4];
+static bool g_bwd_ev_made = false;
+static int g_bwd_calls = 0;
+extern "C" int snf_debug_time_backward(int on) {
+  g_time_bwd = on != 0;
+  if (g_time_bwd && !g_bwd_ev_made) {
+    for (int s = 0; s < BWD_EV_SETS; ++s)
+      for (int i = 0; i < 4; ++i) cudaEventCreate(&g_bwd_ev[s][i]);
+    g_bwd_ev_made = true;
+  }
+  g_bwd_calls = 0;
+  return 0;
+}
+// out[0..2] = summed milliseconds of the dgrad chain, the wgrad and the output-layer gradient kernel over the (at most
+// BWD_EV_SETS most recent) timed calls; returns how many calls were summed
+extern "C" int snf_debug_backward_ms(double *out) {
+  for (int i = 0; i < 3; ++i) out[i] = 0.0;
+  const int n = g_bwd_calls < BWD_EV_SETS ? g_bwd_calls : BWD_EV_SETS;
+  if (!g_bwd_ev_made || n == 0) return 0;
+  cudaDeviceSynchronize();
+  for (int s = 0; s < n; ++s)
+    for (int i = 0; i < 3; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, g_bwd_ev[s][i], g_bwd_ev[s][i + 1]); out[i] += ms; }
+  return n;
+}
+#define BWD_EV(i) do { if (g_time_bwd) cudaEventRecord(g_bwd_ev[g_bwd_calls % BWD_EV_SETS][i], st); } while (0)
+
 // SNF_DEBUG_SYNC=1: synchronise after every backward kernel and name the one that failed (debug aid only)
 static int debug_sync(const char *what, cudaStream_t st) {
   static int on = -1;
@@ -626,7 +656,9 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   dp.save_pre = w.pre; dp.save_d = w.d;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   grid &= ~1;
+  BWD_EV(0);
   bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, st>>>(dp);
+  BWD_EV(1);
   if (int e = debug_sync("mlp_dgrad_bf16_kernel", st)) return e;
 
   bf::WgradParams wp{};
@@ -641,10 +673,13 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   for (int l = 0; l < bf::NH; ++l) { wp.gW[l] = gW[l]; wp.gB[l] = gB[l]; }
   int wgrid = wp.num_items < npairs ? wp.num_items * 2 : npairs * 2;
   bf::mlp_wgrad_bf16_kernel<<<wgrid, bf::WG_THREADS, bf::WG_SMEM_BYTES, st>>>(wp);
+  BWD_EV(2);
   if (int e = debug_sync("mlp_wgrad_bf16_kernel", st)) return e;
 
   const int ogrid = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
   bf::out_wgrad_bf16_kernel<<<ogrid, bf::OW_THREADS, 0, st>>>(dp.g, M, num_tiles, w.h, gW[bf::NH], gB[bf::NH]);
+  BWD_EV(3);
+  if (g_time_bwd) ++g_bwd_calls;
   count_launch(3);
   return launch_status();
 }

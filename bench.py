@@ -239,6 +239,10 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     mlp_events.clear()
+    from sunerf_b200 import _lib as _snf_lib
+    import ctypes as _ct
+    if args.precision == 'bf16':
+        _snf_lib.lib().snf_debug_time_backward(1)     # per-kernel events inside snf_mlp_bwd_bf16 (no host sync)
     clocks.mark_start()
     l0 = ops.launch_count()
     ms = timed_loop(step_resident, args.steps)
@@ -246,6 +250,22 @@ def main():
     mlp_ms = sum(a.elapsed_time(bb) for a, bb, _ in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
     fwd_ms = sum(a.elapsed_time(bb) for a, bb, t in mlp_events if t == 'fwd') / max(1, args.steps)
     bwd_ms = mlp_ms - fwd_ms
+    kernels = None
+    if args.precision == 'bf16':
+        buf = (_ct.c_double * 3)()
+        ncalls = _snf_lib.lib().snf_debug_backward_ms(buf)
+        _snf_lib.lib().snf_debug_time_backward(0)
+        if ncalls > 0:
+            per_step = [buf[i] / ncalls * 2 for i in range(3)]          # two backward calls (fine + coarse network) per step
+            pts = N * (S_COARSE + S_FINE)
+            flop = {'mlp_fwd_bf16_kernel<train>': pts * FLOP_FWD_POINT, 'mlp_dgrad_bf16_kernel': pts * 7 * 2 * 512 * 512,
+                    'mlp_wgrad_bf16_kernel': pts * (84 + 7 * 512) * 512 * 2}
+            kms = {'mlp_fwd_bf16_kernel<train>': fwd_ms, 'mlp_dgrad_bf16_kernel': per_step[0], 'mlp_wgrad_bf16_kernel': per_step[1]}
+            kernels = [{'kernel': k, 'launches_per_step': 2, 'ms_per_step': kms[k], 'algorithmic_flop_per_step': flop[k],
+                        'achieved_tflops': flop[k] / (kms[k] * 1e-3) / 1e12, 'frac': flop[k] / (kms[k] * 1e-3) / 1e12 / pk['tflops']}
+                       for k in kms]
+            kernels.append({'kernel': 'out_wgrad_bf16_kernel', 'launches_per_step': 2, 'ms_per_step': per_step[2], 'bound': 'hbm',
+                            'algorithmic_bytes_per_step': pts * 1024, 'achieved_GBs': pts * 1024 / (per_step[2] * 1e-3) / 1e9})
     ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
     for _ in range(2):
         step_e2e()
@@ -298,7 +318,7 @@ def main():
             'roofline': {'bound': 'tensor', 'kernel': f'field-network MLP forward+backward ({args.precision})',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'traffic': traffic, 'peak_source': pk['src'] + ' (sustained cuBLAS bf16: the kernels run inside a long step)',
-                         'launches_per_step': 6 if args.precision == 'bf16' else None,
+                         'launches_per_step': 6 if args.precision == 'bf16' else None, 'kernels': kernels,
                          'forward': {'ms_per_step': fwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_FWD_POINT / (fwd_ms * 1e-3) / 1e12},
                          'backward': {'ms_per_step': bwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_BWD_POINT / (bwd_ms * 1e-3) / 1e12},
                          'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / (ms / args.steps),

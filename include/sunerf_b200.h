@@ -128,6 +128,12 @@ int snf_adam_step(float *params, const float *grads, float *exp_avg, float *exp_
                   float beta1, float beta2, float eps, int64_t step, float clip_norm, float grad_scale,
                   float *scratch, float *norm_out, void *stream);
 
+/* Measurement aid (bench.py): per-kernel CUDA-event timing of snf_mlp_bwd_bf16 on its launch stream.
+ * snf_debug_time_backward(1) arms it and clears the sums, snf_debug_backward_ms(out[3]) returns the number of timed calls
+ * and the summed milliseconds of {dgrad chain, wgrad, output-layer gradient}.  Off by default. */
+int snf_debug_time_backward(int on);
+int snf_debug_backward_ms(double *out_ms);
+
 #ifdef __cplusplus
 }
 #endif
