@@ -37,8 +37,7 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
   float my_far = fadd(r_obs, D);                                                  // :84
   if (hit == hit) my_far = hit;                                                   // :87-88
   const int nr = (int)(N - ray0 < rpw ? N - ray0 : rpw);
-#pragma unroll 4
-  for (int r = 0; r < nr; ++r) {
+  auto do_ray = [&](int r, const float (&tr)[NJ > 0 ? NJ : 1]) {
     const float z_near = __shfl_sync(kFull, my_near, r), z_far = __shfl_sync(kFull, my_far, r);
     const float p0 = __shfl_sync(kFull, o0, r), p1 = __shfl_sync(kFull, o1, r), p2 = __shfl_sync(kFull, o2, r);
     const float e0 = __shfl_sync(kFull, d0, r), e1 = __shfl_sync(kFull, d1, r), e2 = __shfl_sync(kFull, d2, r);
@@ -46,12 +45,13 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
       const float t = __ldg(t_vals + k);
       return fadd(fmul(z_near, fsub(1.f, t)), fmul(z_far, t));
     };
-    auto sample = [&](int j, float tr, int64_t row) {
+    const int64_t row = (ray0 + r) * S;
+    auto sample = [&](int j, float trj) {
       float z = bin_edge(j);
       if (t_rand != nullptr) {                                                    // :93-98
         const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
         const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
-        z = fadd(lo, fmul(fsub(hi, lo), tr));
+        z = fadd(lo, fmul(fsub(hi, lo), trj));
       }
       __stcs(z_out + row + j, z);
       if (pts_out != nullptr) {                                                   // :100
@@ -60,16 +60,30 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
         pts_out[3 * (row + j) + 2] = fadd(p2, fmul(e2, z));
       }
     };
-    const int64_t row = (ray0 + r) * S;
-    if (NJ > 0) {   // S == 32 NJ: every load of the row is issued before the first use
-      float tr[NJ > 0 ? NJ : 1];
+    if (NJ > 0) {
 #pragma unroll
-      for (int k = 0; k < NJ; ++k) tr[k] = t_rand != nullptr ? __ldcs(t_rand + row + k * 32 + lane) : 0.f;
-#pragma unroll
-      for (int k = 0; k < NJ; ++k) sample(k * 32 + lane, tr[k], row);
+      for (int k = 0; k < NJ; ++k) sample(k * 32 + lane, tr[k]);
     } else {
-      for (int j = lane; j < S; j += 32) sample(j, t_rand != nullptr ? __ldcs(t_rand + row + j) : 0.f, row);
+      for (int j = lane; j < S; j += 32) sample(j, t_rand != nullptr ? __ldcs(t_rand + row + j) : 0.f);
     }
+  };
+  if constexpr (NJ > 0) {
+    // S == 32 NJ: the jitter of RB rays is loaded before any of them is processed (RB x NJ x 128 B in flight per warp)
+    constexpr int RB = 8;
+    for (int r0 = 0; r0 < nr; r0 += RB) {
+      float tr[RB][NJ > 0 ? NJ : 1];
+#pragma unroll
+      for (int b = 0; b < RB; ++b)
+#pragma unroll
+        for (int k = 0; k < NJ; ++k)
+          tr[b][k] = (t_rand != nullptr && r0 + b < nr) ? __ldcs(t_rand + (ray0 + r0 + b) * S + k * 32 + lane) : 0.f;
+#pragma unroll
+      for (int b = 0; b < RB; ++b)
+        if (r0 + b < nr) do_ray(r0 + b, tr[b]);
+    }
+  } else {
+    const float none[NJ > 0 ? NJ : 1] = {};
+    for (int r = 0; r < nr; ++r) do_ray(r, none);
   }
 }
 
