@@ -90,10 +90,39 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
 // ------------------------------------------------------------------------------------------------
 // K2: one warp per ray.  The ray's z, bin centres, CDF and the new samples live in the warp's slice of
 // shared memory; the CDF is a warp scan in double (bit-equal to torch's CPU cumsum, which accumulates in
-// double: every partial sum of these 62 addends is exactly representable, so association is irrelevant),
-// the inverse CDF is a binary search per new sample, and the 64+128 merge is a rank merge (two binary
-// searches) with a sortedness check and an odd-even-sort fallback so the result always equals torch.sort.
+// double: every partial sum of these 62 addends is exactly representable, so association is irrelevant).
+// The three searches of the reference (searchsorted of u in the CDF, and the two rank searches of the
+// 64 + 128 merge that torch.sort performs) are O(1) per element instead of a binary search each:
+//   first[j] = #{k : u_k < cdf_j}        arithmetic guess on the uniform u grid, corrected against the real u values
+//   inds[k]  = #{j : cdf_j <= u_k} = #{j : first[j] <= k}                    -> histogram of first[] + prefix sum
+//   a[j]     = #{k : new_z_k < z_j}      the samples of bin j are k in [first[j-1], first[j]): short search there,
+//                                        corrected against the real new_z values
+//   b[k]     = #{j : z_j <= new_z_k} = #{j : a[j] <= k}                      -> histogram of a[] + prefix sum
+// Every count is verified against the actual values, so the result equals searchsorted / torch.sort exactly for any
+// ascending u; a sortedness check falls back to an odd-even transposition sort (NaNs, rounding at a bin edge).
 // ------------------------------------------------------------------------------------------------
+// exclusive... inclusive prefix sum over cnt[0..n) -> out[k] = sum_{f<=k} cnt[f]; lane owns PER consecutive entries
+template <int PER>
+__device__ __forceinline__ void warp_prefix_counts(const int *cnt, int n, int lane, int (&out)[PER]) {
+  int run = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane * PER + i;
+    run += k < n ? cnt[k] : 0;
+    out[i] = run;
+  }
+  int incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int excl = incl - run;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) out[i] += excl;
+}
+
+template <int PER>   // PER = ceil(n_new / 32): new samples per lane (consecutive k)
 __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_vals,
                                                    const float *__restrict__ weights,
                                                    const float *__restrict__ u, const float *__restrict__ cdf_in,
@@ -103,13 +132,20 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (ray >= N) return;  // whole warp exits together; only __syncwarp below
   const int T = S + n_new;
-  float *zs = sm + (size_t)warp * (3 * S + n_new + T);
+  // CTA-wide: the u grid; per warp: zs[S] bins[S] cdf[S] nz[n_new] comb[T] | first[S] a[S] cnt[max(S, n_new) + 2]
+  float *us = sm;
+  for (int k = threadIdx.x; k < n_new; k += blockDim.x) us[k] = u[k];
+  __syncthreads();
+  if (ray >= N) return;  // whole warp exits together; only __syncwarp below
+  const int ncnt = (S > n_new ? S : n_new) + 2;
+  float *zs = sm + n_new + (size_t)warp * (3 * S + n_new + T + 2 * S + ncnt);
   float *bins = zs + S, *cdf = bins + S, *nz = cdf + S, *comb = nz + n_new;
+  int *first = reinterpret_cast<int *>(comb + T), *arank = first + S, *cnt = arank + S;
   const int nc = S - 1;  // CDF length == number of bin centres
 
-  for (int j = lane; j < S; j += 32) zs[j] = z_vals[ray * S + j];
+  for (int j = lane; j < S; j += 32) zs[j] = __ldcs(z_vals + ray * S + j);
+  for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;
   __syncwarp();
   for (int j = lane; j < nc; j += 32) bins[j] = fmul(.5f, fadd(zs[j + 1], zs[j]));   // :118
   if (cdf_in != nullptr) {
@@ -118,7 +154,7 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
     const float *w = weights + ray * S + 1;  // weights[..., 1:-1]  :119
     const int nw = S - 2;
     double part = 0.0;
-    for (int j = lane; j < nw; j += 32) part += (double)fadd(w[j], 1e-5f);
+    for (int j = lane; j < nw; j += 32) part += (double)fadd(__ldcs(w + j), 1e-5f);
     const float total = (float)warp_sum(part);                                       // :134
     double carry = 0.0;
     for (int base = 0; base < nw; base += 32) {                                      // :137
@@ -134,24 +170,40 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   if (cdf_out != nullptr)
     for (int j = lane; j < nc; j += 32) cdf_out[ray * nc + j] = cdf[j];
 
-  for (int k = lane; k < n_new; k += 32) {
-    const float uu = u[k];
-    int lo = 0, hi = nc;                       // searchsorted(right=True): #{cdf <= u}   :149
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
-    }
-    const int below = max(lo - 1, 0), above = min(lo, nc - 1);                       // :152-153
-    const float cb = cdf[below], ca = cdf[above], bb = bins[below], ba = bins[above];
-    float denom = fsub(ca, cb);                                                      // :164
-    if (denom < 1e-5f) denom = 1.f;                                                  // :165
-    const float t = fdiv(fsub(uu, cb), denom);                                       // :166
-    const float s = fadd(bb, fmul(t, fsub(ba, bb)));                                 // :167
-    nz[k] = s;
-    new_z[ray * n_new + k] = s;
-    if (inds != nullptr) inds[ray * n_new + k] = lo;
+  // ---- first[j] = #{k : u_k < cdf_j} and its histogram
+  for (int j = lane; j < nc; j += 32) {
+    const float c = cdf[j];
+    int k0 = __float2int_ru(c * (float)(n_new - 1));        // exact on the ideal grid k / (n - 1); NaN -> 0
+    k0 = min(max(k0, 0), n_new);
+    while (k0 > 0 && us[k0 - 1] >= c) --k0;
+    while (k0 < n_new && us[k0] < c) ++k0;
+    first[j] = k0;
+    atomicAdd(&cnt[k0], 1);
   }
   __syncwarp();
+  // ---- inds[k] = #{j : cdf_j <= u_k} (searchsorted right=True, :149) and the inverse-CDF samples
+  int ind[PER];
+  warp_prefix_counts<PER>(cnt, n_new, lane, ind);
+  __syncwarp();
+  for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;         // reused for the merge below
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane * PER + i;
+    if (k < n_new) {
+      const float uu = us[k];
+      const int lo = ind[i];
+      const int below = max(lo - 1, 0), above = min(lo, nc - 1);                     // :152-153
+      const float cb = cdf[below], ca = cdf[above], bb = bins[below], ba = bins[above];
+      float denom = fsub(ca, cb);                                                    // :164
+      if (denom < 1e-5f) denom = 1.f;                                                // :165
+      const float t = fdiv(fsub(uu, cb), denom);                                     // :166
+      const float s = fadd(bb, fmul(t, fsub(ba, bb)));                               // :167
+      nz[k] = s;
+      if (inds != nullptr) inds[ray * n_new + k] = lo;
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < n_new; k += 32) __stcs(new_z + ray * n_new + k, nz[k]);     // coalesced copy of the row
 
   // ---- sort(cat(z, new_z))  :123
   bool sorted = true;
@@ -159,23 +211,28 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
   sorted = __all_sync(kFull, sorted);
   if (sorted) {
-    for (int j = lane; j < S; j += 32) {       // rank of z_j: j + #{new_z < z_j}
+    // a[j] = #{k : new_z_k < z_j}: the samples drawn from bin j (inds == j) are k in [first[j-1], first[j])
+    for (int j = lane; j < S; j += 32) {
       const float v = zs[j];
-      int lo = 0, hi = n_new;
+      int lo = j >= 1 ? first[min(j - 1, nc - 1)] : 0, hi = j < nc ? first[j] : n_new;
+      if (hi < lo) hi = lo;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (nz[mid] < v) lo = mid + 1; else hi = mid;
       }
-      comb[j + lo] = v;
+      while (lo > 0 && nz[lo - 1] >= v) --lo;               // exactness does not rest on the bracket
+      while (lo < n_new && nz[lo] < v) ++lo;
+      arank[j] = lo;
+      comb[j + lo] = v;                                     // rank of z_j: j + #{new_z < z_j}
+      atomicAdd(&cnt[lo], 1);
     }
-    for (int k = lane; k < n_new; k += 32) {   // rank of new_z_k: k + #{z <= new_z_k}
-      const float v = nz[k];
-      int lo = 0, hi = S;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (zs[mid] <= v) lo = mid + 1; else hi = mid;
-      }
-      comb[k + lo] = v;
+    __syncwarp();
+    int bk[PER];                                            // b[k] = #{j : z_j <= new_z_k} = #{j : a[j] <= k}
+    warp_prefix_counts<PER>(cnt, n_new, lane, bk);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = lane * PER + i;
+      if (k < n_new) comb[k + bk[i]] = nz[k];               // rank of new_z_k: k + #{z <= new_z_k}
     }
   } else {  // rare: an input is not monotone (rounding at a bin edge, NaN) -> odd-even transposition sort
     for (int j = lane; j < S; j += 32) comb[j] = zs[j];
@@ -190,7 +247,7 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
     }
   }
   __syncwarp();
-  for (int j = lane; j < T; j += 32) z_comb[ray * T + j] = comb[j];
+  for (int j = lane; j < T; j += 32) __stcs(z_comb + ray * T + j, comb[j]);
 }
 
 // query[n,s,:] = (o + d*z, t)
@@ -253,9 +310,15 @@ extern "C" int snf_hier_resample(const float *z_vals, const float *weights, cons
   if (S > 256 || n_new > 512) return SNF_E_SHAPE;
   if (N == 0) return 0;
   const int warps = 4;
-  const size_t smem = (size_t)warps * (3 * S + n_new + S + n_new) * sizeof(float);
-  hier_kernel<<<(unsigned)ceil_div64(N, warps), warps * 32, smem, (cudaStream_t)stream>>>(
-      z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out);
+  const int ncnt = (S > n_new ? S : n_new) + 2;
+  const size_t smem = ((size_t)n_new + (size_t)warps * (3 * S + n_new + (S + n_new) + 2 * S + ncnt)) * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div64(N, warps);
+#define SNF_LAUNCH(PER) \
+  hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out)
+  const int per = (n_new + 31) / 32;
+  if (per <= 1) SNF_LAUNCH(1); else if (per <= 2) SNF_LAUNCH(2); else if (per <= 4) SNF_LAUNCH(4);
+  else if (per <= 8) SNF_LAUNCH(8); else SNF_LAUNCH(16);
+#undef SNF_LAUNCH
   count_launch();
   return launch_status();
 }
