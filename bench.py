@@ -295,6 +295,29 @@ def main():
     renderer.render_observer_image(0.05, 1.0, 3.0, batch_size=RENDER_BATCH, rows=slice(0, 16), as_numpy=False)   # warm-up
     ms_image = timed_loop(image_once, 1)
 
+    # ---- density-temperature config (DT_2012_11.yaml: NeRF_DT + AIA response head, 3072 rays, 7 channels, half of the
+    #      rays with the STEREO channel mask) - reported next to the headline, same fast path
+    del trainer, rend, renderer
+    torch.cuda.empty_cache()
+    torch.manual_seed(7)
+    rend_dt = s.DensityTemperatureRadiativeTransfer(Rs_per_ds=1, model=s.NeRF_DT, pixel_intensity_factor=1e17,
+                                                    model_config={'precision': args.precision}).to(dev)
+    tr_dt = s.RayTrainer(rend_dt)
+    Nd = 3072
+    bd = synthetic_batch(Nd, seed=2)
+    wl = torch.tensor([94., 131., 171., 193., 211., 304., 335.]).repeat(Nd, 1)
+    wl[Nd // 2:] = torch.tensor([0., 0., 171., 193., 211., 304., 0.])            # multi_thermal_loader.py:162-168
+    dd = {k: v.to(dev) for k, v in bd.items()}
+    dd['wl'] = wl.to(dev)
+    dd['target'] = torch.rand(Nd, 7, device=dev)
+
+    def step_dt():
+        return tr_dt.step(dd['rays_o'], dd['rays_d'], dd['times'], dd['target'], dd['wl'])
+    for _ in range(3):
+        step_dt()
+    ms_dt = timed_loop(step_dt, 5) / 5
+    tr_dt.check_finite()
+
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -330,6 +353,8 @@ def main():
                        'image_1024': {'ms': ms_image, 'Msamples_per_s': 1024 * 1024 * (S_COARSE + S_FINE) / (ms_image * 1e-3) / 1e6,
                                       'what': 'ObserverRenderer.render_observer_image, 1024x1024 pixels, rays generated on the '
                                               'device, rows sharded over ranks, no collective'}},
+            'dt_train': {'workload': 'DT_2012_11.yaml: density-temperature SuNeRF train step, 3072 rays/GPU, C=7 (half STEREO-masked)',
+                         'rays_per_s': Nd * world / (ms_dt * 1e-3), 'ms_per_step': ms_dt},
             'clocks': clk}
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline()
