@@ -71,6 +71,7 @@ _PROTOS = {
     'snf_version': (_I, []),
     'snf_error_string': (_c.c_char_p, [_I]),
     'snf_launch_count': (_L, []),
+    'snf_count_launches': (None, [_L]),
     'snf_stratified_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
     'snf_hier_resample': (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
     'snf_image_rays': (_I, [_P, _I, _I, _D, _D, _D, _D, _L, _L, _P, _P, _P]),
@@ -89,6 +90,7 @@ _PROTOS = {
     'snf_composite_dt_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     'snf_render_epilogue': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _P, _F, _P, _P]),
     'snf_train_loss': (_I, [_P, _P, _P, _P, _L, _I, _L, _I, _F, _F, _F, _P, _P, _P, _P, _P]),
+    'snf_adam_step_sched': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P, _P, _P]),
     'snf_debug_time_backward': (_I, [_I]),
     'snf_debug_backward_ms': (_I, [_P]),
     'snf_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _F, _P, _P, _P]),

@@ -274,6 +274,7 @@ using namespace snf;
 
 extern "C" int snf_version(void) { return SNF_VERSION; }
 extern "C" int64_t snf_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" void snf_count_launches(int64_t n) { count_launch((int)n); }   // kernels launched by a CUDA-graph replay
 extern "C" const char *snf_error_string(int code) {
   switch (code) {
     case 0: return "ok";

@@ -287,5 +287,14 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, scratch,
                                         float(grad_scale), scratch.data_ptr(), norm_out.data_ptr(), _stream()), 'snf_adam_step')
 
 
+def adam_step_sched(params, grads, exp_avg, exp_avg_sq, sched, scratch, norm_out, beta1=0.9, beta2=0.999, eps=1e-8,
+                    clip_norm: float = 0.5, grad_scale: float = 1.0) -> None:
+    """adam_step with {lr, step, gamma, lr_floor} (float64[4]) on the device: replayable inside a CUDA graph."""
+    _lib.check(_lib.lib().snf_adam_step_sched(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                              params.numel(), sched.data_ptr(), beta1, beta2, eps, float(clip_norm),
+                                              float(grad_scale), scratch.data_ptr(), norm_out.data_ptr(), _stream()),
+               'snf_adam_step_sched')
+
+
 def launch_count() -> int:
     return int(_lib.lib().snf_launch_count())

@@ -14,7 +14,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import ops, parallel
+from . import _lib, ops, parallel
 from ._lib import SnfError
 from .rendering import DensityTemperatureRadiativeTransfer, SuNeRFRendering
 
@@ -40,7 +40,7 @@ def _align4(n: int) -> int:
 class RayTrainer:
     def __init__(self, rendering: SuNeRFRendering, lr: float = 1e-4, lr_end: float = 1e-5, lr_iterations: float = 1e6,
                  clip_norm: float = 0.5, lambda_image: float = 1.0, lambda_regularization: float = 1.0,
-                 asinh_a: float = 0.005, process_group=None, device=None):
+                 asinh_a: float = 0.005, process_group=None, device=None, use_cuda_graph: bool = False):
         self.r = rendering
         self.dt = isinstance(rendering, DensityTemperatureRadiativeTransfer)
         self.dev = torch.device(device) if device is not None else next(rendering.parameters()).device
@@ -57,6 +57,12 @@ class RayTrainer:
         self.grad_norm = torch.zeros(1, device=self.dev)
         self.finite_flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self._side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        # CUDA-graph replay of the whole step (the NCCL all-reduces of the multi-GPU step are captured with it).
+        # lr / step live on the device so that nothing on the host changes between replays.
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._device_sched = self.use_cuda_graph       # once the schedule lives on the device it stays there (eager steps too)
+        self.sched = torch.tensor([lr, 1.0, self.gamma, 5e-5], device=self.dev, dtype=torch.float64)
+        self._graph, self._g_in, self._g_out, self._g_key, self._g_warm = None, None, None, None, 0
 
     # -- flat parameter / gradient buffers: [fine model | coarse model], log_abs contiguous in channel order
     def _flatten(self):
@@ -107,6 +113,51 @@ class RayTrainer:
 
     @torch.no_grad()
     def step(self, rays_o, rays_d, times, target, wavelengths=None, t_rand=None) -> Dict[str, torch.Tensor]:
+        """One training step. With use_cuda_graph the step is captured once per batch shape (after two eager warm-up
+        steps) and replayed: inputs are copied into static buffers, the returned tensors are static buffers too."""
+        if not self.use_cuda_graph:
+            return self._step_impl(rays_o, rays_d, times, target, wavelengths, t_rand, device_sched=self._device_sched)
+        if t_rand is None and self.r.sampler.perturb:      # the reference's torch.rand draw, outside the graph
+            t_rand = torch.rand((rays_o.shape[0], self.r.sampler.t_vals.shape[1]), device=self.dev)
+        ins = {'rays_o': rays_o, 'rays_d': rays_d, 'times': times, 'target': target}
+        if wavelengths is not None:
+            ins['wavelengths'] = wavelengths
+        if t_rand is not None:
+            ins['t_rand'] = t_rand
+        key = tuple((k, tuple(v.shape)) for k, v in ins.items())
+        if key != self._g_key:
+            self._graph, self._g_key, self._g_warm = None, key, 0
+        if self._graph is None and self._g_warm < 2:       # warm-up: lazy allocations / one-time attribute calls
+            self._g_warm += 1
+            return self._step_impl(rays_o, rays_d, times, target, wavelengths, t_rand, device_sched=True)
+        if self._graph is None:
+            self._g_in = {k: v.detach().to(self.dev, torch.float32).contiguous().clone() for k, v in ins.items()}
+            torch.cuda.synchronize(self.dev)
+            self._graph = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(self._graph):
+                gi = self._g_in
+                self._g_out = self._step_impl(gi['rays_o'], gi['rays_d'], gi['times'], gi['target'], gi.get('wavelengths'),
+                                              gi.get('t_rand'), device_sched=True, host_bookkeeping=False)
+            self._g_launches = ops.launch_count() - l0     # kernels per replay (they were recorded, not executed)
+            _lib.lib().snf_count_launches(-self._g_launches)
+            # the capture itself did not execute: fall through to the first replay with the caller's data
+        for k, v in ins.items():
+            self._g_in[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        _lib.lib().snf_count_launches(self._g_launches)
+        self._host_bookkeeping()
+        return self._g_out
+
+    def _host_bookkeeping(self):
+        self.step_count += 1
+        for name in ('fine_model', 'coarse_model'):   # packed bf16 weights must be refreshed next forward
+            getattr(self.r, name)._pack_key = None
+        if self.lr > 5e-5:                             # sunerf.py:36-40
+            self.lr *= self.gamma
+
+    def _step_impl(self, rays_o, rays_d, times, target, wavelengths=None, t_rand=None, device_sched=False,
+                   host_bookkeeping=True) -> Dict[str, torch.Tensor]:
         r = self.r
         N = rays_o.shape[0]
         z, _ = r.sampler.sample_z(rays_o, rays_d, t_rand=t_rand)
@@ -160,13 +211,17 @@ class RayTrainer:
         h_coarse = self._reduce_async('coarse_model')
         parallel.wait_all([h_fine, h_coarse])
         # ---- optimiser (grads averaged over ranks == Lightning dp's mean of replica losses)
-        self.step_count += 1
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.scratch,
-                      self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
-        for name in ('fine_model', 'coarse_model'):   # packed bf16 weights must be refreshed next forward
-            getattr(r, name)._pack_key = None
-        if self.lr > 5e-5:                             # sunerf.py:36-40
-            self.lr *= self.gamma
+        if device_sched:
+            ops.adam_step_sched(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.sched, self.scratch,
+                                self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
+        else:
+            ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count + 1, self.lr, self.scratch,
+                          self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
+        if host_bookkeeping:
+            self._host_bookkeeping()
+        else:                                          # under capture: the next replay must re-pack the weights
+            for name in ('fine_model', 'coarse_model'):
+                getattr(r, name)._pack_key = None
         return {'losses': losses, 'coarse_image': img_c, 'fine_image': img_f, 'grad_norm': self.grad_norm,
                 'z_vals_hierarchical': new_z}
 

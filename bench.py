@@ -133,6 +133,7 @@ def workload_config(gpus):
     return {'workload': 'emission_2012_08-193.yaml: emission SuNeRF train step, 2 x (84->512x8->2) sine MLP, 64+128 samples/ray',
             'rays_per_gpu': RAYS_PER_GPU, 'global_rays': RAYS_PER_GPU * gpus, 'samples_per_ray': S_COARSE + S_FINE,
             'parallelism': f'ray-shard dp{gpus}, one NCCL all-reduce of the flat fp32 gradient per step',
+            'launch': 'whole step captured once and replayed as a CUDA graph (RayTrainer(use_cuda_graph=True))',
             'l2': 'per-step working set (saved layer activations, >1 GB) exceeds the 126 MB L2; no explicit flush'}
 
 
@@ -167,6 +168,7 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--ref-rays', type=int, default=128)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~27 kernels of a step one by one instead of replaying a graph')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -185,7 +187,7 @@ def main():
 
     torch.manual_seed(7)                      # run_density_temperature.py:17; same init on every rank (no broadcast)
     rend = s.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'precision': args.precision}).to(dev)
-    trainer = s.RayTrainer(rend)
+    trainer = s.RayTrainer(rend, use_cuda_graph=not args.no_cuda_graph)
     N = RAYS_PER_GPU
     b = synthetic_batch(N * world, seed=0)    # global batch, sharded by rank: rank r owns rays [r*N, (r+1)*N)
     host = {k: v[rank * N:(rank + 1) * N].contiguous().pin_memory() for k, v in b.items()}
@@ -203,7 +205,6 @@ def main():
             mlp_events.append((e0, e1, tag))
             return r
         return w
-    ops.mlp_forward, ops.mlp_backward = timed(_fwd, 'fwd'), timed(_bwd, 'bwd')
 
     def step_resident():
         t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
@@ -238,15 +239,25 @@ def main():
         clocks.start()
     for _ in range(args.warmup):
         step_resident()
+    clocks.mark_start()
+    l0 = ops.launch_count()
+    ms = timed_loop(step_resident, args.steps)          # the headline: the step replayed as one CUDA graph (unless --no-cuda-graph)
+    launches = ops.launch_count() - l0
+    # ---- roofline pass: the same K steps launched kernel by kernel, so that CUDA events can bracket the field-network
+    #      launches on their stream (events cannot be read back from inside a replayed graph); same kernels, same data
+    graphed = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    ops.mlp_forward, ops.mlp_backward = timed(_fwd, 'fwd'), timed(_bwd, 'bwd')
+    for _ in range(2):
+        step_resident()
     mlp_events.clear()
     from sunerf_b200 import _lib as _snf_lib
     import ctypes as _ct
     if args.precision == 'bf16':
         _snf_lib.lib().snf_debug_time_backward(1)     # per-kernel events inside snf_mlp_bwd_bf16 (no host sync)
-    clocks.mark_start()
-    l0 = ops.launch_count()
-    ms = timed_loop(step_resident, args.steps)
-    launches = ops.launch_count() - l0
+    ms_eager = timed_loop(step_resident, args.steps)
+    trainer.use_cuda_graph = graphed
+    ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
     mlp_ms = sum(a.elapsed_time(bb) for a, bb, _ in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
     fwd_ms = sum(a.elapsed_time(bb) for a, bb, t in mlp_events if t == 'fwd') / max(1, args.steps)
     bwd_ms = mlp_ms - fwd_ms
@@ -266,7 +277,6 @@ def main():
                        for k in kms]
             kernels.append({'kernel': 'out_wgrad_bf16_kernel', 'launches_per_step': 2, 'ms_per_step': per_step[2], 'bound': 'hbm',
                             'algorithmic_bytes_per_step': pts * 1024, 'achieved_GBs': pts * 1024 / (per_step[2] * 1e-3) / 1e9})
-    ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
     for _ in range(2):
         step_e2e()
     ms_e2e = timed_loop(step_e2e, args.steps)
@@ -344,7 +354,11 @@ def main():
                          'launches_per_step': 6 if args.precision == 'bf16' else None, 'kernels': kernels,
                          'forward': {'ms_per_step': fwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_FWD_POINT / (fwd_ms * 1e-3) / 1e12},
                          'backward': {'ms_per_step': bwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_BWD_POINT / (bwd_ms * 1e-3) / 1e12},
-                         'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / (ms / args.steps),
+                         'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / (ms_eager / args.steps),
+                         'timing': 'CUDA events around the field-network launches (torch current stream = launch stream) in an '
+                                   'eager pass of the same K steps run right after the timed region; the timed region itself '
+                                   + ('replays the step as one CUDA graph' if graphed else 'is launched eagerly too'),
+                         'eager_ms_per_step': ms_eager / args.steps,
                          'algorithmic_flop_per_step': N * FLOP_TRAIN_RAY},
             'render': {'metric': 'render_Msamples_per_s', 'value': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_render * 1e-3) / 1e6,
                        'unit': 'Msamples/s', 'rays_per_batch': RENDER_BATCH, 'ms_per_batch': ms_render,

@@ -30,6 +30,8 @@ int snf_version(void);
 const char *snf_error_string(int code);
 /* number of kernel launches issued through this library by the calling process (bench.py gpu_launches) */
 int64_t snf_launch_count(void);
+/* a CUDA-graph replay launches the captured kernels without passing through this library: the host adds them here */
+void snf_count_launches(int64_t n);
 
 /* ---- a1: StratifiedSampler.forward, sunerf/train/sampling.py:68-102 -------------------------------
  * t_vals[S] is the sampler buffer (linspace(0,1,S)); t_rand[N,S] is the torch.rand draw of :97, or NULL
@@ -127,6 +129,13 @@ int snf_train_loss(const float *coarse, const float *fine, const float *target, 
 int snf_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int64_t step, float clip_norm, float grad_scale,
                   float *scratch, float *norm_out, void *stream);
+
+/* Same step with the schedule resident on the device (CUDA-graph replay: no host scalar changes between launches).
+ * sched = {lr, step (starts at 1), gamma, lr_floor} as doubles; after the update the step is advanced and lr is multiplied
+ * by gamma while lr > lr_floor - the per-batch ExponentialLR rule of sunerf/model/sunerf.py:36-40. */
+int snf_adam_step_sched(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, double *sched,
+                        float beta1, float beta2, float eps, float clip_norm, float grad_scale, float *scratch,
+                        float *norm_out, void *stream);
 
 /* Measurement aid (bench.py): per-kernel CUDA-event timing of snf_mlp_bwd_bf16 on its launch stream.
  * snf_debug_time_backward(1) arms it and clears the sums, snf_debug_backward_ms(out[3]) returns the number of timed calls

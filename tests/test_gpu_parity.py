@@ -452,6 +452,31 @@ def test_ray_trainer_bf16_reduces_the_loss():
     tr.check_finite()
 
 
+def test_ray_trainer_cuda_graph_replay_matches_eager():
+    """The captured-and-replayed step (device-resident lr/step schedule) follows the eager step exactly: same kernels,
+    same inputs -> same losses, same parameters after 6 steps (2 eager warm-ups, capture, 4 replays)."""
+    import sunerf_b200 as s
+    g, ra = _emission_module('bf16')
+    _, rb = _emission_module('bf16')
+    ta, tb = s.RayTrainer(ra, lr=1e-3), s.RayTrainer(rb, lr=1e-3, use_cuda_graph=True)
+    args = (t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['target']))
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    l0 = s.ops.launch_count()
+    for i in range(6):
+        tr_ = torch.rand(g['t_rand'].shape, device='cuda', generator=gen)
+        a = ta.step(*args, t_rand=tr_)
+        b = tb.step(*args, t_rand=tr_)
+        # the wgrad accumulates with floating-point atomics: two runs agree to rounding, not bit for bit
+        assert torch.allclose(a['losses'], b['losses'], rtol=2e-3, atol=1e-7), (i, a['losses'], b['losses'])
+    assert (ta.flat - tb.flat).abs().max().item() <= 2.5e-3          # 6 Adam steps of at most lr = 1e-3 each
+    assert torch.nn.functional.cosine_similarity(ta.flat.double(), tb.flat.double(), dim=0).item() > 0.99999
+    assert tb._graph is not None and abs(tb.lr - ta.lr) < 1e-18 and tb.step_count == ta.step_count == 6
+    assert abs(tb.sched[0].item() - tb.lr) < 1e-15 and tb.sched[1].item() == 7.0
+    per_step = (s.ops.launch_count() - l0) / 12
+    assert 20 <= per_step <= 40, per_step          # replays are counted like eager launches
+    tb.check_finite()
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_emission_1024_rays():
     """BASELINE config sizes (1024 rays, 64+192 samples): size-independent invariants instead of oracle runs."""
