@@ -115,8 +115,12 @@ class RayTrainer:
     def step(self, rays_o, rays_d, times, target, wavelengths=None, t_rand=None) -> Dict[str, torch.Tensor]:
         """One training step. With use_cuda_graph the step is captured once per batch shape (after two eager warm-up
         steps) and replayed: inputs are copied into static buffers, the returned tensors are static buffers too."""
+        # host (pinned) tensors are accepted: eager steps move them to the device, replays copy them straight into the
+        # graph's static input buffers
+        to_dev = lambda x: x if (x is None or x.is_cuda) else x.to(self.dev, non_blocking=True)
         if not self.use_cuda_graph:
-            return self._step_impl(rays_o, rays_d, times, target, wavelengths, t_rand, device_sched=self._device_sched)
+            return self._step_impl(to_dev(rays_o), to_dev(rays_d), to_dev(times), to_dev(target), to_dev(wavelengths),
+                                   to_dev(t_rand), device_sched=self._device_sched)
         if t_rand is None and self.r.sampler.perturb:      # the reference's torch.rand draw, outside the graph
             t_rand = torch.rand((rays_o.shape[0], self.r.sampler.t_vals.shape[1]), device=self.dev)
         ins = {'rays_o': rays_o, 'rays_d': rays_d, 'times': times, 'target': target}
@@ -129,7 +133,8 @@ class RayTrainer:
             self._graph, self._g_key, self._g_warm = None, key, 0
         if self._graph is None and self._g_warm < 2:       # warm-up: lazy allocations / one-time attribute calls
             self._g_warm += 1
-            return self._step_impl(rays_o, rays_d, times, target, wavelengths, t_rand, device_sched=True)
+            return self._step_impl(to_dev(rays_o), to_dev(rays_d), to_dev(times), to_dev(target), to_dev(wavelengths),
+                                   to_dev(t_rand), device_sched=True)
         if self._graph is None:
             self._g_in = {k: v.detach().to(self.dev, torch.float32).contiguous().clone() for k, v in ins.items()}
             torch.cuda.synchronize(self.dev)

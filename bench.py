@@ -210,10 +210,9 @@ def main():
         t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
         return trainer.step(devb['rays_o'], devb['rays_d'], devb['times'], devb['target'], t_rand=t_rand)
 
-    def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    def step_e2e():                         # the public call with HOST (pinned) buffers: the H2D copies are part of the step
         t_rand = torch.rand((N, S_COARSE), device=dev, generator=gen)
-        res = trainer.step(d['rays_o'], d['rays_d'], d['times'], d['target'], t_rand=t_rand)
+        res = trainer.step(host['rays_o'], host['rays_d'], host['times'], host['target'], t_rand=t_rand)
         return res['losses'].cpu()          # device->host read of the step's result (synchronises)
 
     def barrier():
