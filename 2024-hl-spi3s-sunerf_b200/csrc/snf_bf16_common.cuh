@@ -77,7 +77,7 @@ constexpr int OFF_BIAS = OFF_RING + NSTAGE * WHALF_BYTES;
 constexpr int OFF_WOUT = OFF_BIAS + 2 * BIAS_BYTES;
 constexpr int OFF_OSUM = OFF_WOUT + WOUT_BYTES;
 constexpr int OFF_BAR = OFF_OSUM + (EPI_GROUPS - 1) * TILE_M * 8;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_BAR + 512;
 static_assert(SMEM_BYTES <= 232448, "layer-chain kernels exceed the 227 KB shared-memory window");
 //   full[s] / empty[s] : weight ring, as in Bars
 //   acc[h]             : temporal N-half h (output columns [256h, 256h+256)) of the current layer accumulated
@@ -93,6 +93,10 @@ struct Bars {
   __device__ uint32_t tmem_slot() const { return base + 8u * (2 * NSTAGE + 7); }
 };
 constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
+// [quarter (4)][slot (8)] u32 arrival counters: the last warp of a quarter to finish a slab (slot = slab index) issues its
+// TMA store.  Between two quarter barriers every slot is used at most once, so arrivals of different events never mix.
+constexpr int OFF_QCNT = OFF_BAR + 256;
+static_assert(8 * (2 * NSTAGE + 8) <= 256, "barrier block overlaps the counters");
 }  // namespace fw
 
 // saved-image workspace (training): [enc][H = sin(pre)][D = dL/dpre] as [tile][layer][128 KB] bf16 images and

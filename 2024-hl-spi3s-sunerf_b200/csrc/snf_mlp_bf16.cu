@@ -136,6 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     fence_barrier_init();
+    for (int k = 0; k < 32; ++k) *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::OFF_QCNT + 4 * k) = 0;
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
   for (int i = threadIdx.x; i < D; i += NTHREADS) bias_s[i] = __ldg(bias_all + i);
@@ -269,19 +270,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // the quarter's 32 rows of slabs [sl0, sl0+nsl) are complete in the A image: one elected lane TMA-stores them
+    // The quarter's 32 rows of slabs [sl0, sl0+nsl) are written (and fenced) by this warp: the LAST of the quarter's warps
+    // to get here TMA-stores them.  No blocking barrier on the per-step path: an acq_rel counter in shared memory.
     const uint64_t stream_pol = l2_policy_evict_first();   // saved activations: written once, read by the backward much later
+    const uint32_t qcnt = base + fw::OFF_QCNT + 32 * q;   // + 4 * slot
     auto store_quarter = [&](uint8_t *img, int sl0, int nsl) {
-      named_bar_sync(2 + q, QUAD_THREADS);
-      if (g == 0 && lane == 0) {
+      __syncwarp();
+      if (lane == 0 && (smem_counter_arrive(qcnt + 4 * (sl0 & 7)) % EPI_GROUPS) == EPI_GROUPS - 1) {
         for (int sl = sl0; sl < sl0 + nsl; ++sl)
           bulk_s2g_hint(img + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
         bulk_commit();
       }
     };
+    PROF_DECL(t_stw);
     auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
-      if (g == 0 && lane == 0) bulk_wait_read_all();
+      PROF_T0(t0);
+      if (lane == 0) bulk_wait_read_all();            // any warp of the quarter may have issued some of them
       named_bar_sync(2 + q, QUAD_THREADS);
+      PROF_ADD(t_stw, t0);
     };
     uint32_t ph = 0;
     PROF_DECL(t_acc0); PROF_DECL(t_acc1); PROF_DECL(t_enc); PROF_T0(t_begin);
@@ -333,15 +339,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         fence_proxy_async_smem();
         tcgen05_fence_before();
         arrive_ready(0);
-        if (TRAIN) {   // the quarter's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
-          named_bar_sync(2 + q, QUAD_THREADS);
-          if (g == 0 && lane == 0) {
-            uint8_t *esave = p.save_enc + (int64_t)tile * 2 * SLAB_BYTES + q * PAIR_BYTES;
-            bulk_s2g_hint(esave, sA + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-            bulk_s2g_hint(esave + SLAB_BYTES, sA + SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-            bulk_commit();
-          }
-        }
+        if (TRAIN)     // the quarter's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
+          store_quarter(p.save_enc + (int64_t)tile * 2 * SLAB_BYTES, 0, 2);
         PROF_ADD(t_enc, t0);
       }
       // ---- layers
@@ -448,13 +447,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         }
       }
     }
-    if (TRAIN && g == 0 && lane == 0) bulk_wait_all();
+    if (TRAIN && lane == 0) bulk_wait_all();
 #ifdef SNF_PROF
     if (e == 0 && lane == 0) {
       g_prof[TRAIN][blockIdx.x * 8 + 3] = clock64() - t_begin;
       g_prof[TRAIN][blockIdx.x * 8 + 4] = t_acc0;
       g_prof[TRAIN][blockIdx.x * 8 + 5] = t_acc1;
       g_prof[TRAIN][blockIdx.x * 8 + 6] = t_enc;
+      g_prof[TRAIN][blockIdx.x * 8 + 7] = t_stw;
     }
 #endif
   }

@@ -78,6 +78,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     fence_barrier_init();
+    for (int k = 0; k < 32; ++k) *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::OFF_QCNT + 4 * k) = 0;
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
   if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
@@ -192,20 +193,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
       return cosq_get(w, i & 3);
     };
-    // hand complete slabs to the MMA issuer first (ready barrier k, or none), then store them for the wgrad
+    // hand complete slabs to the MMA issuer first (ready barrier k, or none), then store them for the wgrad: the LAST of
+    // the quarter's warps to get here issues the TMA store (acq_rel counter, no blocking barrier on the per-step path)
     const uint64_t stream_pol = l2_policy_evict_first();
+    const uint32_t qcnt = base + fw::OFF_QCNT + 32 * q;   // + 4 * slot
     auto publish = [&](uint8_t *dimg, int sl0, int nsl, int k) {
       fence_proxy_async_smem();
       if (k >= 0) { tcgen05_fence_before(); arrive_ready(k); }
-      named_bar_sync(2 + q, QUAD_THREADS);
-      if (g == 0 && lane == 0) {
+      __syncwarp();
+      if (lane == 0 && (smem_counter_arrive(qcnt + 4 * (sl0 & 7)) % EPI_GROUPS) == EPI_GROUPS - 1) {
         for (int sl = sl0; sl < sl0 + nsl; ++sl)
           bulk_s2g_hint(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
         bulk_commit();
       }
     };
     auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
-      if (g == 0 && lane == 0) bulk_wait_read_all();
+      if (lane == 0) bulk_wait_read_all();            // any warp of the quarter may have issued some of them
       named_bar_sync(2 + q, QUAD_THREADS);
     };
     uint32_t ph = 0;
@@ -315,7 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         ph ^= 1;
       }
     }
-    if (g == 0 && lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   cluster_sync_all();

@@ -21,11 +21,11 @@ L.snf_debug_prof.restype = ctypes.c_int
 L.snf_debug_prof.argtypes = [ctypes.c_void_p]
 assert L.snf_debug_prof(buf) == 0
 a = np.array(buf, dtype=np.int64).reshape(2, 148, 8)
-names = ['issuer total', 'issuer wait ready', 'issuer wait full', 'epi total', 'epi wait acc0', 'epi wait acc1', 'epi enc', '-']
+names = ['issuer total', 'issuer wait ready', 'issuer wait full', 'epi total', 'epi wait acc0', 'epi wait acc1', 'epi enc', 'epi wait stores']
 for which, tag in ((0, 'inference (last launch: fine pass, 4096 rays)'), (1, 'training (last launch: fine pass, 1024 rays)')):
     print(tag)
     lead = a[which, 0::2]
-    for i, n in enumerate(names[:7]):
+    for i, n in enumerate(names[:8]):
         v = lead[:, i]
         print(f'  {n:20s} mean {v.mean():12.0f}  min {v.min():12d}  max {v.max():12d}')
 tb = (ctypes.c_longlong * (4 * 512))()
