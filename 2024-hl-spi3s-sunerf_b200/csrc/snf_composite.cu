@@ -517,9 +517,19 @@ __global__ void __launch_bounds__(256)
     bad |= !finite_f(r);
     sr += r;
   }
+  // block-level reduction first: three atomics per block instead of three per warp on the same three addresses
+  __shared__ float red[3][8];
   sc = warp_sum_f(sc); sf = warp_sum_f(sf); sr = warp_sum_f(sr);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], sc); atomicAdd(&acc[1], sf); atomicAdd(&acc[2], sr); }
-  if (bad) atomicOr(finite_flag, 1);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = sc; red[1][w] = sf; red[2][w] = sr; }
+  const bool any_bad = __syncthreads_or(bad);
+  if (w == 0 && l < 3) {
+    float t = 0.f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) t += red[l][i];
+    atomicAdd(&acc[l], t);
+  }
+  if (any_bad && threadIdx.x == 0) atomicOr(finite_flag, 1);
 }
 
 // acc aliases losses+1 (no __restrict__): all three sums are read before anything is written

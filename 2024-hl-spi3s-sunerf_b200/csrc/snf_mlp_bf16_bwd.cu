@@ -679,7 +679,7 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   BWD_EV(2);
   if (int e = debug_sync("mlp_wgrad_bf16_kernel", st)) return e;
 
-  const int ogrid = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
+  const int ogrid = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;   // latency-bound stream: fewer CTAs measured slower
   bf::out_wgrad_bf16_kernel<<<ogrid, bf::OW_THREADS, 0, st>>>(dp.g, M, num_tiles, w.h, gW[bf::NH], gB[bf::NH]);
   BWD_EV(3);
   if (g_time_bwd) ++g_bwd_calls;
