@@ -529,6 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
 // instruction, 8 rows (independent 16 B loads) in flight per thread; partial sums stay in registers over all the
 // tiles of the CTA, are combined across the row groups in shared memory and leave as one atomic per output.
 constexpr int OW_THREADS = 256;
+constexpr int OW_ROWS = 8;       // rows (independent 16 B loads) in flight per thread (16 measured slower)
 __global__ void __launch_bounds__(OW_THREADS) out_wgrad_bf16_kernel(const float2 *__restrict__ g, int64_t M, int num_tiles,
                                                                     const uint8_t *__restrict__ save_h,
                                                                     float *__restrict__ gW, float *__restrict__ gB) {
@@ -541,18 +542,18 @@ __global__ void __launch_bounds__(OW_THREADS) out_wgrad_bf16_kernel(const float2
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     const uint8_t *h7 = save_h + ((int64_t)t * NH + (NH - 1)) * A_BYTES + slab * SLAB_BYTES;
 #pragma unroll 1
-    for (int r0 = rg * 32; r0 < rg * 32 + 32; r0 += 8) {
-      uint4 hv[8];
-      float2 gg[8];
+    for (int r0 = rg * 32; r0 < rg * 32 + 32; r0 += OW_ROWS) {
+      uint4 hv[OW_ROWS];
+      float2 gg[OW_ROWS];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < OW_ROWS; ++i) {
         const int r = r0 + i;
         const int64_t m = (int64_t)t * TILE_M + r;
         hv[i] = __ldcs(reinterpret_cast<const uint4 *>(h7 + sw128_chunk_off(r, c8)));
         gg[i] = m < M ? __ldg(g + m) : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < OW_ROWS; ++i) {
         const float h[8] = {bf_lo(hv[i].x), bf_hi(hv[i].x), bf_lo(hv[i].y), bf_hi(hv[i].y),
                             bf_lo(hv[i].z), bf_hi(hv[i].z), bf_lo(hv[i].w), bf_hi(hv[i].w)};
 #pragma unroll
