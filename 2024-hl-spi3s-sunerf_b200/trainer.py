@@ -227,7 +227,9 @@ class RayTrainer:
         else:                                          # under capture: the next replay must re-pack the weights
             for name in ('fine_model', 'coarse_model'):
                 getattr(r, name)._pack_key = None
-        return {'losses': losses, 'coarse_image': img_c, 'fine_image': img_f, 'grad_norm': self.grad_norm,
+        # what the reference logs per step (sunerf.py:121-129): loss, coarse, fine, regularization, psnr = -10 log10(fine)
+        psnr = -10. * torch.log10(losses[2])
+        return {'losses': losses, 'psnr': psnr, 'coarse_image': img_c, 'fine_image': img_f, 'grad_norm': self.grad_norm,
                 'z_vals_hierarchical': new_z}
 
     def _reduce_async(self, name):
