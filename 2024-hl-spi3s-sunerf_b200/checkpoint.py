@@ -56,11 +56,28 @@ def _stub_for(module: str, name: str) -> type:
     return _STUBS[key]
 
 
+class _Opaque:
+    """Stands in for an object of a third-party package that is not installed (e.g. the xitorch interpolators the
+    reference's density-temperature module keeps in `self.response`): keeps whatever state the pickle carries."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {'_state': state})
+
+
+_OPAQUE: Dict[str, type] = {}
+
+
 class _RefUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == 'sunerf' or module.startswith('sunerf.'):
             return _stub_for(module, name)
-        return super().find_class(module, name)
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            key = f'{module}.{name}'
+            if key not in _OPAQUE:
+                _OPAQUE[key] = type(name, (_Opaque,), {'_ref_name': key})
+            return _OPAQUE[key]
 
 
 class _RefPickle:

@@ -26,6 +26,19 @@ def test_save_state_snf_loads_without_the_reference_package():
     assert param_digest(r) == str(golden('ckpt_expected.npz')['digest'])     # every tensor, bit for bit
 
 
+def test_density_temperature_save_state_loads_without_xitorch():
+    """The reference DT module pickles xitorch Interp1D objects (self.response) next to the networks: they become opaque
+    stand-ins, the rebuilt module carries NeRF_DT weights, the 7 absorption scalars and the volumetric constants."""
+    import sunerf_b200 as s
+    assert 'xitorch' not in sys.modules
+    state = s.checkpoint.load_save_state(os.path.join(GOLDEN, 'ref_save_state_dt.snf'))
+    r = state['rendering']
+    assert isinstance(r, s.DensityTemperatureRadiativeTransfer) and isinstance(r.fine_model, s.NeRF_DT)
+    assert r.pixel_intensity_factor == 1e17 and r.sampler.perturb is False
+    assert abs(float(r.fine_model.log_absortpion['335'].detach()) - 7e-6) < 1e-12
+    assert param_digest(r) == str(golden('ckpt_expected_dt.npz')['digest'])
+
+
 def test_lightning_ckpt_loads_into_a_fresh_module():
     import sunerf_b200 as s
     r = s.EmissionRadiativeTransfer(Rs_per_ds=1, sampling_config={'type': 'stratified', 'perturb': False},
@@ -57,3 +70,16 @@ def test_loaded_reference_checkpoint_renders_like_the_reference():
     for k in ('coarse_image', 'fine_image'):
         assert rel_err(out[k], g['out.' + k]) <= 2e-5, (k, rel_err(out[k], g['out.' + k]))
     assert (out['regularization'].cpu() - torch.from_numpy(g['out.regularization'])).abs().max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_loaded_reference_dt_checkpoint_renders_like_the_reference():
+    import sunerf_b200 as s
+    g = golden('ckpt_expected_dt.npz')
+    r = s.checkpoint.load_save_state(os.path.join(GOLDEN, 'ref_save_state_dt.snf'), precision='fp32')['rendering'].cuda()
+    with torch.no_grad():
+        out = r(t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['wavelengths']))
+    for k in ('coarse_image', 'fine_image'):
+        ref = torch.from_numpy(g['out.' + k])
+        assert ((out[k].cpu() - ref).abs() <= 4e-5 * ref.abs() + 1e-12).all(), (k, rel_err(out[k], ref, 1e-9))
+    assert (out['fine_image'].cpu()[20:, 0] == 0).all()          # STEREO-masked channels render exactly 0
