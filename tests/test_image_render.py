@@ -98,3 +98,25 @@ def test_observer_renderer_against_oracle_and_under_sharding():
     # resolution override keeps the field of view (Map.resample semantics)
     out_half = r.render_observer_image(lat, lon, time, resolution=(6, 5))
     assert out_half['fine_image'].shape == (6, 5, 1)
+
+
+@pytest.mark.gpu
+def test_observer_renderer_density_temperature_channels():
+    """render_mhd.yaml shape of call: SimpleStar field, 6 AIA channels, wavelengths broadcast over the batch."""
+    import sunerf_b200 as s
+    H, W, plate = 8, 6, 400.0
+    wl = [94, 171, 193, 211, 304, 335]
+    rend = s.DensityTemperatureRadiativeTransfer(Rs_per_ds=1, model=s.SimpleStar, pixel_intensity_factor=1e10,
+                                                 sampling_config={'type': 'stratified', 'perturb': False}).cuda()
+    with torch.no_grad():
+        for m in (rend.coarse_model, rend.fine_model):
+            for c in orc.AIA_CHANNELS:
+                m.log_absortpion[str(c)].fill_(1e-6)      # the default 19-20 makes the star opaque: image == 0
+    r = s.ObserverRenderer(rend, (H, W), plate)
+    out = r.render_observer_image(0.1, 2.0, 0.0, wl=wl, batch_size=20)
+    assert out['fine_image'].shape == (H, W, 6) and np.isfinite(out['fine_image']).all() and (out['fine_image'] > 0).any()
+    c2w = s.image_render.pose_spherical(-2.0, 0.1, s.rays.R_OBS)
+    ro, rd = s.ops.image_rays(c2w, H, W, plate, 'cuda')
+    with torch.no_grad():
+        ref = rend(ro, rd, torch.zeros(H * W, 1, device='cuda'), torch.tensor(wl, dtype=torch.float32, device='cuda').repeat(H * W, 1))
+    assert np.array_equal(out['fine_image'].reshape(-1, 6), ref['fine_image'].cpu().numpy())
