@@ -53,6 +53,8 @@ def allreduce_sum_async(flat_grad: torch.Tensor, lo: int, hi: int, group=None):
     """Launch the all-reduce of one contiguous gradient bucket; returns a work handle (None when world == 1)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
+    if os.environ.get('SNF_DEBUG_NO_ALLREDUCE') == '1':      # measurement aid: what the exchange step costs (wrong gradients!)
+        return None
     return dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
 
 
