@@ -91,12 +91,14 @@ struct Bars {
   __device__ uint32_t acc(int h) const { return base + 8u * (2 * NSTAGE + h); }
   __device__ uint32_t ready(int k) const { return base + 8u * (2 * NSTAGE + 2 + k); }
   __device__ uint32_t tmem_slot() const { return base + 8u * (2 * NSTAGE + 7); }
+  // training / dgrad, local to each CTA: wrote[slot] = all epilogue warps have written (and fenced) the slab(s) of this
+  // event into the A image (slot 0: slabs 0-3 at once or the encoder image, slot k: slab k); afree = the store warp's
+  // TMA stores of the previous layer have finished reading the A image
+  __device__ uint32_t wrote(int slot) const { return base + 8u * (2 * NSTAGE + 8 + slot); }
+  __device__ uint32_t afree() const { return base + 8u * (2 * NSTAGE + 16); }
 };
 constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
-// [quarter (4)][slot (8)] u32 arrival counters: the last warp of a quarter to finish a slab (slot = slab index) issues its
-// TMA store.  Between two quarter barriers every slot is used at most once, so arrivals of different events never mix.
-constexpr int OFF_QCNT = OFF_BAR + 256;
-static_assert(8 * (2 * NSTAGE + 8) <= 256, "barrier block overlaps the counters");
+static_assert(8 * (2 * NSTAGE + 17) <= 512, "barrier block");
 }  // namespace fw
 
 // saved-image workspace (training): [enc][H = sin(pre)][D = dL/dpre] as [tile][layer][128 KB] bf16 images and

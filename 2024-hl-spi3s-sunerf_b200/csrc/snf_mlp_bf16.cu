@@ -135,8 +135,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
     mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
+    for (int k = 0; k < 8; ++k) mbar_init(bar.wrote(k), N_EPI_WARPS);
+    mbar_init(bar.afree(), 1);
     fence_barrier_init();
-    for (int k = 0; k < 32; ++k) *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::OFF_QCNT + 4 * k) = 0;
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
   for (int i = threadIdx.x; i < D; i += NTHREADS) bias_s[i] = __ldg(bias_all + i);
@@ -240,6 +241,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         }
       }
     }
+  } else if (TRAIN && warp == 2 && lane == 0) {
+    // =========================== store warp (training): TMA-stores every finished slab of the A image (the encoder
+    // image, then h_l of each layer) for the backward.  The epilogue warps only arrive on wrote[] (non-blocking): the
+    // issue latency of the bulk stores - they back up behind the HBM writes - stays off the epilogue's critical path.
+    const uint64_t stream_pol = l2_policy_evict_first();   // written once, read by the backward much later
+    uint32_t wph = 0;
+    auto wait_wrote = [&](int slot) { mbar_wait(bar.wrote(slot), (wph >> slot) & 1u); wph ^= 1u << slot; };
+    auto store_slabs = [&](uint8_t *img, int sl0, int nsl) {
+      for (int sl = sl0; sl < sl0 + nsl; ++sl) bulk_s2g_hint(img + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES, stream_pol);
+      bulk_commit();
+    };
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+      const int tile = tp * 2 + (int)rank;
+      wait_wrote(0);
+      store_slabs(p.save_enc + (int64_t)tile * 2 * SLAB_BYTES, 0, 2);
+      bulk_wait_read_all();
+      mbar_arrive(bar.afree());                         // the encoder image may be overwritten by h_0
+      for (int l = 0; l < NH; ++l) {
+        uint8_t *hsave = p.save_h + ((int64_t)tile * NH + l) * A_BYTES;
+        wait_wrote(0);
+        store_slabs(hsave, 0, 4);
+        for (int j = 0; j < 4; ++j) { wait_wrote(4 + j); store_slabs(hsave, 4 + j, 1); }
+        bulk_wait_read_all();
+        mbar_arrive(bar.afree());                       // h_l has left the A image
+      }
+    }
+    bulk_wait_all();
   }
   } else {
     reg_alloc<REGS_EPI>();
@@ -270,23 +298,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // The quarter's 32 rows of slabs [sl0, sl0+nsl) are written (and fenced) by this warp: the LAST of the quarter's warps
-    // to get here TMA-stores them.  No blocking barrier on the per-step path: an acq_rel counter in shared memory.
-    const uint64_t stream_pol = l2_policy_evict_first();   // saved activations: written once, read by the backward much later
-    const uint32_t qcnt = base + fw::OFF_QCNT + 32 * q;   // + 4 * slot
-    auto store_quarter = [&](uint8_t *img, int sl0, int nsl) {
+    // Training: after a slab (or slabs 0-3 / the encoder image) is written and fenced, the warp arrives on the CTA-local
+    // wrote[slot] barrier - the store warp issues the TMA stores - and before the A image is overwritten it waits for
+    // afree (the previous layer's stores have finished reading it; normally long complete).
+    auto arrive_wrote = [&](int slot) {
       __syncwarp();
-      if (lane == 0 && (smem_counter_arrive(qcnt + 4 * (sl0 & 7)) % EPI_GROUPS) == EPI_GROUPS - 1) {
-        for (int sl = sl0; sl < sl0 + nsl; ++sl)
-          bulk_s2g_hint(img + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-        bulk_commit();
-      }
+      if (lane == 0) mbar_arrive(bar.wrote(slot));
     };
+    uint32_t aph = 0;
+    bool first_tile = true;
     PROF_DECL(t_stw);
-    auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
+    auto wait_afree = [&]() {
       PROF_T0(t0);
-      if (lane == 0) bulk_wait_read_all();            // any warp of the quarter may have issued some of them
-      named_bar_sync(2 + q, QUAD_THREADS);
+      mbar_wait(bar.afree(), aph); aph ^= 1;
       PROF_ADD(t_stw, t0);
     };
     uint32_t ph = 0;
@@ -307,7 +331,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M) xv = p.x[m];
         const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
-        if (TRAIN) wait_quarter_stores();             // the previous tile's last layer must have left the A image
+        if (TRAIN && !first_tile) wait_afree();       // the previous tile's last layer must have left the A image
+        first_tile = false;
         auto put8 = [&](int feat0, float a, float b, float c, float d) {   // 4 consecutive features (8 bytes)
           const int c8 = feat0 >> 3;
           *reinterpret_cast<uint2 *>(gA + (c8 >> 3) * SLAB_BYTES + sw128_chunk_off(row, c8 & 7) + (feat0 & 7) * 2) =
@@ -339,8 +364,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         fence_proxy_async_smem();
         tcgen05_fence_before();
         arrive_ready(0);
-        if (TRAIN)     // the quarter's 32 rows of both encoder slabs are contiguous 4 KB blocks of the image
-          store_quarter(p.save_enc + (int64_t)tile * 2 * SLAB_BYTES, 0, 2);
+        if (TRAIN) arrive_wrote(0);                   // the store warp saves the encoder image (slabs 0, 1)
         PROF_ADD(t_enc, t0);
       }
       // ---- layers
@@ -348,7 +372,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
       for (int l = 0; l < NH; ++l) {
         const bool last = (l == NH - 1);
         const float *bl = bias_s + (l & 1) * D;
-        uint8_t *hsave = TRAIN ? p.save_h + ((int64_t)tile * NH + l) * A_BYTES : nullptr;
         uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * C_BYTES : nullptr;
         uint32_t held[4 * CPT / 2];                   // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
         float o0 = 0.f, o1 = 0.f;
@@ -369,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
             for (int i = et; i < D; i += N_EPI) bias_s[(ln & 1) * D + i] = __ldg(bias_all + ln * D + i);
           } else if (!last || TRAIN) {
             // all MMAs of layer l are complete: the A image may be overwritten with h_l, half 0 first (from registers)
-            if (TRAIN) wait_quarter_stores();         // ... once the stores of h_{l-1} (or of the encoder image) have read it
+            if (TRAIN) wait_afree();                  // ... once the stores of h_{l-1} (or of the encoder image) have read it
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -382,7 +405,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               tcgen05_fence_before();
               arrive_ready(0);
             }
-            if (TRAIN) store_quarter(hsave, 0, 4);
+            if (TRAIN) arrive_wrote(0);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -427,7 +450,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                   tcgen05_fence_before();
                   arrive_ready(1 + j);
                 }
-                if (TRAIN) store_quarter(hsave, sl, 1);   // h_l for the weight gradients
+                if (TRAIN) arrive_wrote(sl);              // h_l for the weight gradients
               }
             }
           }
@@ -447,7 +470,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         }
       }
     }
-    if (TRAIN && lane == 0) bulk_wait_all();
 #ifdef SNF_PROF
     if (e == 0 && lane == 0) {
       g_prof[TRAIN][blockIdx.x * 8 + 3] = clock64() - t_begin;

@@ -77,8 +77,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar.full(s), rank == 0 ? 2 : 1); mbar_init(bar.empty(s), 1); }
     mbar_init(bar.acc(0), 1); mbar_init(bar.acc(1), 1);
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
+    for (int k = 0; k < 8; ++k) mbar_init(bar.wrote(k), N_EPI_WARPS);
+    mbar_init(bar.afree(), 1);
     fence_barrier_init();
-    for (int k = 0; k < 32; ++k) *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::OFF_QCNT + 4 * k) = 0;
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
   if (warp == 1) tmem_alloc_2cta(bar.tmem_slot(), 512);
@@ -161,6 +162,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         }
       }
     }
+  } else if (warp == 2 && lane == 0) {
+    // =========================== store warp: TMA-stores every finished slab of the A image (dpre_7 .. dpre_0) for the
+    // wgrad; the epilogue warps only arrive on wrote[] (see the forward kernel)
+    const uint64_t stream_pol = l2_policy_evict_first();
+    uint32_t wph = 0;
+    auto wait_wrote = [&](int slot) { mbar_wait(bar.wrote(slot), (wph >> slot) & 1u); wph ^= 1u << slot; };
+    auto store_slabs = [&](uint8_t *img, int sl0, int nsl) {
+      for (int sl = sl0; sl < sl0 + nsl; ++sl) bulk_s2g_hint(img + sl * SLAB_BYTES, sA + sl * SLAB_BYTES, SLAB_BYTES, stream_pol);
+      bulk_commit();
+    };
+    for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
+      const int tile = tp * 2 + (int)rank;
+      uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
+      for (int sl = 0; sl < 8; ++sl) { wait_wrote(sl); store_slabs(d_tile + (int64_t)(NH - 1) * A_BYTES, sl, 1); }
+      bulk_wait_read_all();
+      mbar_arrive(bar.afree());                         // dpre_7 has left the A image
+      for (int l = NH - 1; l >= 1; --l) {
+        uint8_t *dprev = d_tile + (int64_t)(l - 1) * A_BYTES;
+        wait_wrote(0);
+        store_slabs(dprev, 0, 4);
+        for (int j = 0; j < 4; ++j) { wait_wrote(4 + j); store_slabs(dprev, 4 + j, 1); }
+        bulk_wait_read_all();
+        mbar_arrive(bar.afree());
+      }
+    }
+    bulk_wait_all();
   }
   } else {
     reg_alloc<REGS_EPI>();
@@ -193,39 +220,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
       return cosq_get(w, i & 3);
     };
-    // hand complete slabs to the MMA issuer first (ready barrier k, or none), then store them for the wgrad: the LAST of
-    // the quarter's warps to get here issues the TMA store (acq_rel counter, no blocking barrier on the per-step path)
-    const uint64_t stream_pol = l2_policy_evict_first();
-    const uint32_t qcnt = base + fw::OFF_QCNT + 32 * q;   // + 4 * slot
-    auto publish = [&](uint8_t *dimg, int sl0, int nsl, int k) {
+    // hand complete slabs to the MMA issuer first (ready barrier k, or none), then to the store warp (wrote[slot])
+    auto publish = [&](int slot, int k) {
       fence_proxy_async_smem();
       if (k >= 0) { tcgen05_fence_before(); arrive_ready(k); }
       __syncwarp();
-      if (lane == 0 && (smem_counter_arrive(qcnt + 4 * (sl0 & 7)) % EPI_GROUPS) == EPI_GROUPS - 1) {
-        for (int sl = sl0; sl < sl0 + nsl; ++sl)
-          bulk_s2g_hint(dimg + sl * SLAB_BYTES + q * PAIR_BYTES, sA + sl * SLAB_BYTES + q * PAIR_BYTES, PAIR_BYTES, stream_pol);
-        bulk_commit();
-      }
+      if (lane == 0) mbar_arrive(bar.wrote(slot));
     };
-    auto wait_quarter_stores = [&]() {                // the quarter's earlier stores have finished reading the A image
-      if (lane == 0) bulk_wait_read_all();            // any warp of the quarter may have issued some of them
-      named_bar_sync(2 + q, QUAD_THREADS);
-    };
+    uint32_t aph = 0;
+    bool first_tile = true;
+    auto wait_afree = [&]() { mbar_wait(bar.afree(), aph); aph ^= 1; };   // the previous stores have read the A image
     uint32_t ph = 0;
     for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
       const int tile = tp * 2 + (int)rank;
       const int64_t m = (int64_t)tile * TILE_M + row;
       const uint8_t *pre_tile = p.save_pre + (int64_t)tile * NH * C_BYTES;
-      uint8_t *d_tile = p.save_d + (int64_t)tile * NH * A_BYTES;
       uint4 pn[NQ];
       // ---- dpre_7 = (g0 W_out[0,:] + g1 W_out[1,:]) * cos(pre_7), written straight into the A image
       {
         const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * C_BYTES;
-        uint8_t *d7 = d_tile + (int64_t)(NH - 1) * A_BYTES;
         load_pre(p7, 0, pn);
         float2 gg = make_float2(0.f, 0.f);
         if (m < p.M) gg = p.g[m];
-        wait_quarter_stores();                        // the previous tile's last stores have left the A image
+        if (!first_tile) wait_afree();                // the previous tile's last stores have left the A image
+        first_tile = false;
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
           uint4 pv[NQ];
@@ -245,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * cos_of(pv, 8 * c + 6), (gg.x * wa1.w + gg.y * wb1.w) * cos_of(pv, 8 * c + 7));
             *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) = o;
           }
-          publish(d7, sl, 1, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
+          publish(sl, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
         }
       }
 #pragma unroll 1
@@ -254,7 +272,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         const bool last = (l == 1);
         const uint8_t *pprev = pre_tile + (int64_t)(l - 1) * C_BYTES;
         const uint8_t *pnext = pre_tile + (int64_t)(l >= 2 ? l - 2 : 0) * C_BYTES;
-        uint8_t *dprev = d_tile + (int64_t)(l - 1) * A_BYTES;
         uint32_t held[4 * CPT / 2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -264,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           tmem_ld16(tm_row + h * 256, accA);
           if (h == 1) {
             // all MMAs of layer l are complete: the A image may be overwritten with dpre_{l-1}, half 0 from registers
-            wait_quarter_stores();                    // ... once the stores of dpre_l have read it
+            wait_afree();                             // ... once the stores of dpre_l have read it
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -272,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
                 *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
                     make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
                                held[(CPT / 2) * j + 4 * c + 3]);
-            publish(dprev, 0, 4, last ? -1 : 0);
+            publish(0, last ? -1 : 0);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -311,14 +328,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
               for (int c = 0; c < CHUNKS; ++c)
                 *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-              publish(dprev, sl, 1, last ? -1 : 1 + j);
+              publish(sl, last ? -1 : 1 + j);
             }
           }
         }
         ph ^= 1;
       }
     }
-    if (lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   cluster_sync_all();
