@@ -133,7 +133,8 @@ def workload_config(gpus):
     return {'workload': 'emission_2012_08-193.yaml: emission SuNeRF train step, 2 x (84->512x8->2) sine MLP, 64+128 samples/ray',
             'rays_per_gpu': RAYS_PER_GPU, 'global_rays': RAYS_PER_GPU * gpus, 'samples_per_ray': S_COARSE + S_FINE,
             'parallelism': f'ray-shard dp{gpus}, one NCCL all-reduce of the flat fp32 gradient per step',
-            'launch': 'whole step captured once and replayed as a CUDA graph (RayTrainer(use_cuda_graph=True))',
+            'launch': 'whole step captured once and replayed as a CUDA graph (RayTrainer(use_cuda_graph=True)); the coarse '
+                      'network\'s backward runs on a side stream beside the fine one (roofline pass: serial)',
             'l2': 'per-step working set (saved layer activations, >1 GB) exceeds the 126 MB L2; no explicit flush'}
 
 
@@ -168,6 +169,7 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--ref-rays', type=int, default=128)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--serial-backward', action='store_true', help='coarse backward after the fine one instead of beside it (A/B aid)')
     ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~27 kernels of a step one by one instead of replaying a graph')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -188,6 +190,7 @@ def main():
     torch.manual_seed(7)                      # run_density_temperature.py:17; same init on every rank (no broadcast)
     rend = s.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'precision': args.precision}).to(dev)
     trainer = s.RayTrainer(rend, use_cuda_graph=not args.no_cuda_graph)
+    trainer.overlap_backward = not args.serial_backward
     N = RAYS_PER_GPU
     b = synthetic_batch(N * world, seed=0)    # global batch, sharded by rank: rank r owns rays [r*N, (r+1)*N)
     host = {k: v[rank * N:(rank + 1) * N].contiguous().pin_memory() for k, v in b.items()}
@@ -246,6 +249,7 @@ def main():
     #      launches on their stream (events cannot be read back from inside a replayed graph); same kernels, same data
     graphed = trainer.use_cuda_graph
     trainer.use_cuda_graph = False
+    trainer.overlap_backward = False                   # one kernel at a time, so that each is timed alone
     ops.mlp_forward, ops.mlp_backward = timed(_fwd, 'fwd'), timed(_bwd, 'bwd')
     for _ in range(2):
         step_resident()
@@ -256,6 +260,7 @@ def main():
         _snf_lib.lib().snf_debug_time_backward(1)     # per-kernel events inside snf_mlp_bwd_bf16 (no host sync)
     ms_eager = timed_loop(step_resident, args.steps)
     trainer.use_cuda_graph = graphed
+    trainer.overlap_backward = not args.serial_backward
     ops.mlp_forward, ops.mlp_backward = _fwd, _bwd
     mlp_ms = sum(a.elapsed_time(bb) for a, bb, _ in mlp_events) / max(1, args.steps)   # per step: 2 fwd + 2 bwd groups
     fwd_ms = sum(a.elapsed_time(bb) for a, bb, t in mlp_events if t == 'fwd') / max(1, args.steps)
