@@ -59,8 +59,9 @@ class RayTrainer:
         # CUDA-graph replay of the whole step (the NCCL all-reduces of the multi-GPU step are captured with it).
         # lr / step live on the device so that nothing on the host changes between replays.
         self.use_cuda_graph = bool(use_cuda_graph)
-        self.overlap_backward = True                   # coarse backward on a side stream (off: one kernel at a time)
+        self.overlap_backward = True                   # coarse backward on a side stream beside the fine pass (off: one kernel at a time)
         self._side_stream = torch.cuda.Stream(device=self.dev)
+        self._zero1 = torch.zeros(1, device=self.dev)
         self._device_sched = self.use_cuda_graph       # once the schedule lives on the device it stays there (eager steps too)
         self.sched = torch.tensor([lr, 1.0, self.gamma, 5e-5], device=self.dev, dtype=torch.float64)
         self._graph, self._g_in, self._g_out, self._g_key, self._g_warm = None, None, None, None, 0
@@ -180,6 +181,29 @@ class RayTrainer:
             img_c, wts_c, _ = ops.composite_dt_fwd(raw_c, z, wavelengths, la_c, vc_c, r._table_x, r._table_y, F)
         else:
             img_c, wts_c, _ = ops.composite_emission_fwd(raw_c, z, rays_d)
+        # ---- coarse backward, on a side stream.  The gradient of the coarse image needs the coarse image only, and the
+        # resampled depths carry no gradient, so the coarse network's whole backward is independent of the fine pass: its
+        # CTAs fill the SMs that the fine pass leaves idle - the last round of each persistent kernel (3.46 / 10.4 rounds
+        # of 74 CTA pairs at 1024 rays) and the short HBM-class kernels between the field-network launches.
+        main = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_backward else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            # coarse term of the loss alone (same kernel, same arithmetic: g_ic is bit-identical to the full call's)
+            _, g_ic, _, _ = ops.train_loss(img_c, img_c, target, self._zero1, asinh_scaling=not self.dt,
+                                           asinh_a=self.asinh_a, lambda_image=self.lam_img, lambda_reg=0.0,
+                                           finite_flag=self.finite_flag)
+            gw, gb = self._grads(r.coarse_model)
+            if self.dt:
+                lo, hi = self.la_off_coarse_model, self.vc_off_coarse_model + 4
+                self.flat_grad[lo:hi].zero_()
+                g_raw_c, _, _ = ops.composite_dt_bwd(raw_c, z, wavelengths, la_c, vc_c, r._table_x, r._table_y, F, g_ic, None,
+                                                     self.flat_grad[lo:lo + 7], self.flat_grad[hi - 4:hi - 3])
+            else:
+                g_raw_c = ops.composite_emission_bwd(raw_c, z, rays_d, g_ic.view(-1), None)
+            ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
+        # ---- fine pass
         new_z, z_comb = r.sampler_hierarchical.resample(z, wts_c)
         Sf = z_comb.shape[1]
         q_f = ops.make_query(rays_o, rays_d, z_comb, times)
@@ -191,27 +215,9 @@ class RayTrainer:
             img_f, wts_f, qq = ops.composite_emission_fwd(raw_f, z_comb, rays_d)
         _, _, reg, g_q = ops.render_epilogue(rays_o, rays_d, z_comb, wts_f, qq, r.reg_radius / r.Rs_per_ds, r.kind,
                                              grad_scale=self.lam_reg / float(N * Sf), want_gq=True)
-        losses, g_ic, g_if, _ = ops.train_loss(img_c, img_f, target, reg, asinh_scaling=not self.dt, asinh_a=self.asinh_a,
-                                               lambda_image=self.lam_img, lambda_reg=self.lam_reg,
-                                               finite_flag=self.finite_flag)
-        # ---- backward.  The two networks' backward passes are independent (the resampled depths carry no gradient), so the
-        # coarse one runs on a side stream: its CTAs fill the SMs the fine pass leaves idle in the last round of each
-        # persistent kernel (3.46 / 10.4 rounds of 74 CTA pairs at 1024 rays).  Fine first: its gradient bucket is reduced
-        # while the rest of the coarse pass runs.
-        main = torch.cuda.current_stream()
-        side = self._side_stream if self.overlap_backward else main
-        if side is not main:
-            side.wait_stream(main)
-        with torch.cuda.stream(side):
-            gw, gb = self._grads(r.coarse_model)
-            if self.dt:
-                lo, hi = self.la_off_coarse_model, self.vc_off_coarse_model + 4
-                self.flat_grad[lo:hi].zero_()
-                g_raw_c, _, _ = ops.composite_dt_bwd(raw_c, z, wavelengths, la_c, vc_c, r._table_x, r._table_y, F, g_ic, None,
-                                                     self.flat_grad[lo:lo + 7], self.flat_grad[hi - 4:hi - 3])
-            else:
-                g_raw_c = ops.composite_emission_bwd(raw_c, z, rays_d, g_ic.view(-1), None)
-            ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
+        losses, _, g_if, _ = ops.train_loss(img_c, img_f, target, reg, asinh_scaling=not self.dt, asinh_a=self.asinh_a,
+                                            lambda_image=self.lam_img, lambda_reg=self.lam_reg,
+                                            finite_flag=self.finite_flag)
         gw_f, gb_f = self._grads(r.fine_model)
         if self.dt:
             lo, hi = self.la_off_fine_model, self.vc_off_fine_model + 4
