@@ -170,7 +170,7 @@ def main():
     ap.add_argument('--ref-rays', type=int, default=128)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial-backward', action='store_true', help='coarse backward after the fine one instead of beside it (A/B aid)')
-    ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~27 kernels of a step one by one instead of replaying a graph')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~30 kernels of a step one by one instead of replaying a graph')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
