@@ -28,8 +28,7 @@ constexpr int CPT = 64 / EPI_GROUPS;         // accumulator columns per thread a
 constexpr int CHUNKS = CPT / 8;              // 16-byte chunks of the A image per thread and step
 constexpr int N_EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int N_EPI = N_EPI_WARPS * 32;      // epilogue threads: (row, column group)
-constexpr int QUAD_THREADS = 32 * EPI_GROUPS;   // the warps of one TMEM lane quarter (named barrier 2 + q): they own 32 rows
-constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warps 2-3 idle;
+constexpr int EPI_WARP0 = 4;                 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer / peer relay, warp 2 TMA store warp (training, dgrad);
 constexpr int NTHREADS = 128 + N_EPI;        // the following warpgroups: epilogue.  Registers are re-balanced with setmaxnreg:
 constexpr int REGS_CTRL = 40, REGS_EPI = EPI_GROUPS == 2 ? 232 : 104;   // 128 x CTRL + N_EPI x EPI must fit the launch allocation (NTHREADS x 168 or 96)
 static_assert(EPI_GROUPS == 2 || EPI_GROUPS == 4, "CPT must be 32 or 16 (tcgen05.ld x32 / x16)");

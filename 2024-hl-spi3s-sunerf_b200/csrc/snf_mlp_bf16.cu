@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float *b0, const 
 }
 
 // ------------------------------------------------------------------------------------------ fused forward
-constexpr int PAIR_BYTES = 32 * 128;   // 32 rows of one slab: what the two warps of a TMEM lane quarter own (4 KB, contiguous)
 
 struct FwdParams {
   const float4 *x;        // [M] (x,y,z,t)

@@ -51,7 +51,6 @@ struct DgradParams {
   uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
 };
 
-constexpr int PAIR_BYTES = 32 * 128;   // 32 rows of one slab: what the two warps of a TMEM lane quarter own (4 KB, contiguous)
 
 __device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");

@@ -67,13 +67,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// acq_rel counter in shared memory: "last warp to arrive does the follow-up" without a blocking barrier
-__device__ __forceinline__ uint32_t smem_counter_arrive(uint32_t addr) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
-  return old;
-}
-
 // ---------------------------------------------------------------- TMA bulk copies (UBLKCP)
 // global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
