@@ -546,11 +546,11 @@ using namespace snf;
 
 extern "C" int snf_composite_emission_fwd(const float *raw, const float *z, const float *rays_d, int64_t N, int S,
                                           float *image, float *weights, float *absorption, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(raw); SNF_CHECK_PTR(z); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(image); SNF_CHECK_PTR(weights);
   SNF_CHECK_PTR(absorption); SNF_CHECK_ALIGN(raw, 8);
   if (N < 0 || S < 2) return SNF_E_ARG;
   if (S > 256) return SNF_E_SHAPE;
-  if (N == 0) return 0;
   const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
   const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
 #define SNF_LAUNCH(NCH) \
@@ -567,11 +567,11 @@ extern "C" int snf_composite_emission_fwd(const float *raw, const float *z, cons
 extern "C" int snf_composite_emission_bwd(const float *raw, const float *z, const float *rays_d, int64_t N, int S,
                                           const float *g_image, const float *g_absorption, float *g_raw,
                                           void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(raw); SNF_CHECK_PTR(z); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(g_image); SNF_CHECK_PTR(g_raw);
   SNF_CHECK_ALIGN(raw, 8); SNF_CHECK_ALIGN(g_raw, 8);
   if (N < 0 || S < 2) return SNF_E_ARG;
   if (S > 256) return SNF_E_SHAPE;
-  if (N == 0) return 0;
   const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
   const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
   float2 *g2 = reinterpret_cast<float2 *>(g_raw);
@@ -590,12 +590,12 @@ extern "C" int snf_composite_dt_fwd(const float *inferences, const float *z, con
                                     int S, int C, const float *log_abs, const float *vol_c, const float *table_x,
                                     const float *table_y, float F, float *image, float *weights, float *regq,
                                     void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(inferences); SNF_CHECK_PTR(z); SNF_CHECK_PTR(wavelengths); SNF_CHECK_PTR(log_abs);
   SNF_CHECK_PTR(vol_c); SNF_CHECK_PTR(table_x); SNF_CHECK_PTR(table_y); SNF_CHECK_PTR(image);
   SNF_CHECK_PTR(weights); SNF_CHECK_PTR(regq); SNF_CHECK_ALIGN(inferences, 8);
   if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
   if (S > 256 || C > 8) return SNF_E_SHAPE;
-  if (N == 0) return 0;
   int64_t nblk = ceil_div64(N, kRayWarps);
   if (nblk > 148 * 16) nblk = 148 * 16;             // persistent CTAs: the tables are built once per CTA
   const float2 *inf2 = reinterpret_cast<const float2 *>(inferences);
@@ -615,13 +615,13 @@ extern "C" int snf_composite_dt_bwd(const float *inferences, const float *z, con
                                     int S, int C, const float *log_abs, const float *vol_c, const float *table_x,
                                     const float *table_y, float F, const float *g_image, const float *g_regq,
                                     float *g_inferences, float *g_log_abs, float *g_vol_c, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(inferences); SNF_CHECK_PTR(z); SNF_CHECK_PTR(wavelengths); SNF_CHECK_PTR(log_abs);
   SNF_CHECK_PTR(vol_c); SNF_CHECK_PTR(table_x); SNF_CHECK_PTR(table_y); SNF_CHECK_PTR(g_image);
   SNF_CHECK_PTR(g_inferences); SNF_CHECK_PTR(g_log_abs); SNF_CHECK_PTR(g_vol_c);
   SNF_CHECK_ALIGN(inferences, 8); SNF_CHECK_ALIGN(g_inferences, 8);
   if (N < 0 || S < 3 || C <= 0) return SNF_E_ARG;
   if (S > 256 || C > 8) return SNF_E_SHAPE;
-  if (N == 0) return 0;
   int64_t nblk = ceil_div64(N, kRayWarps);
   if (nblk > 148 * 16) nblk = 148 * 16;
   const float2 *inf2 = reinterpret_cast<const float2 *>(inferences);
@@ -642,10 +642,10 @@ extern "C" int snf_render_epilogue(const float *rays_o, const float *rays_d, con
                                    const float *weights, const float *q, int64_t N, int S, float r0, int kind,
                                    float *height_map, float *absorption_map, float *reg, float reg_grad_scale,
                                    float *g_q, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(z_comb); SNF_CHECK_PTR(weights); SNF_CHECK_PTR(q);
   SNF_CHECK_PTR(height_map); SNF_CHECK_PTR(absorption_map); SNF_CHECK_PTR(reg);
   if (N < 0 || S <= 0 || (kind != 0 && kind != 1)) return SNF_E_ARG;
-  if (N == 0) return 0;
   render_epilogue_kernel<<<(unsigned)ceil_div64(N, kRayWarps), kRayWarps * 32, 0, (cudaStream_t)stream>>>(
       rays_o, rays_d, z_comb, weights, q, N, S, r0, kind, height_map, absorption_map, reg, reg_grad_scale, g_q);
   count_launch();
@@ -654,9 +654,9 @@ extern "C" int snf_render_epilogue(const float *rays_o, const float *rays_d, con
 
 extern "C" int snf_simple_star_fwd(const float *x, int64_t M, float rho_0, float h0, float T0, float R_s,
                                    float t_photosphere, float *out, void *stream) {
+  if (M == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(x); SNF_CHECK_PTR(out); SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8);
   if (M < 0) return SNF_E_ARG;
-  if (M == 0) return 0;
   simple_star_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(x), M, rho_0, h0, T0, R_s, t_photosphere, reinterpret_cast<float2 *>(out));
   count_launch();

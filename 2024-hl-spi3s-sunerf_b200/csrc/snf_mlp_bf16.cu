@@ -537,10 +537,10 @@ static int num_sms() {
 
 extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, float off0, float off1, float *out,
                                 void *ws, int train, void *stream) {
+  if (M == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(x); SNF_CHECK_PTR(packed); SNF_CHECK_PTR(out);
   SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8); SNF_CHECK_ALIGN(packed, 1024);
   if (M < 0) return SNF_E_ARG;
-  if (M == 0) return 0;
   if (train) { SNF_CHECK_PTR(ws); SNF_CHECK_ALIGN(ws, 1024); }
   static bool attr_done = false;
   if (!attr_done) {

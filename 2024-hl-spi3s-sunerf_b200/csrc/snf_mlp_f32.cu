@@ -295,11 +295,11 @@ extern "C" int64_t snf_mlp_ws_bytes(int64_t M, int n_hidden, int d_filter, int m
 extern "C" int snf_mlp_fwd_f32(const float *x, int64_t M, const float *const *W, const float *const *B,
                                int n_hidden, int d, float off0, float off1, float *out, void *ws, int train,
                                void *stream) {
+  if (M == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(x); SNF_CHECK_PTR(W); SNF_CHECK_PTR(B); SNF_CHECK_PTR(out); SNF_CHECK_PTR(ws);
   SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8); SNF_CHECK_ALIGN(ws, 256);
   if (M < 0 || n_hidden < 1 || n_hidden > 16) return SNF_E_ARG;
   if (d % 4 != 0 || d < 4) return SNF_E_SHAPE;
-  if (M == 0) return 0;
   for (int l = 0; l <= n_hidden; ++l) { SNF_CHECK_PTR(W[l]); SNF_CHECK_PTR(B[l]); SNF_CHECK_ALIGN(W[l], 16); SNF_CHECK_ALIGN(B[l], 16); }
   cudaStream_t st = (cudaStream_t)stream;
   F32Ws w = f32_layout(ws, M, n_hidden, d, train);

@@ -288,9 +288,9 @@ extern "C" const char *snf_error_string(int code) {
 extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals,
                                      const float *t_rand, int64_t N, int S, float distance, float solar_R,
                                      float *z_vals, float *points, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(t_vals); SNF_CHECK_PTR(z_vals);
   if (N < 0 || S <= 0) return SNF_E_ARG;
-  if (N == 0) return 0;
   int rpw = 32;                                   // small batches: fewer rays per warp so the grid still fills the GPU
   while (rpw > 1 && N / rpw < 148 * 16) rpw >>= 1;
   const unsigned grid = (unsigned)ceil_div64(N, 8 * rpw);
@@ -305,11 +305,11 @@ extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, c
 extern "C" int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in,
                                  int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds,
                                  float *cdf_out, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(z_vals); SNF_CHECK_PTR(u); SNF_CHECK_PTR(new_z); SNF_CHECK_PTR(z_comb);
   if (weights == nullptr && cdf_in == nullptr) return SNF_E_ARG;
   if (N < 0 || S < 3 || n_new <= 0) return SNF_E_ARG;
   if (S > 256 || n_new > 512) return SNF_E_SHAPE;
-  if (N == 0) return 0;
   const int warps = 4;
   const int ncnt = (S > n_new ? S : n_new) + 2;
   const size_t smem = ((size_t)n_new + (size_t)warps * (3 * S + n_new + (S + n_new) + 2 * S + ncnt)) * sizeof(float);
@@ -326,10 +326,10 @@ extern "C" int snf_hier_resample(const float *z_vals, const float *weights, cons
 
 extern "C" int snf_make_query(const float *rays_o, const float *rays_d, const float *z, const float *times,
                               int64_t N, int S, float *query, void *stream) {
+  if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(z); SNF_CHECK_PTR(times); SNF_CHECK_PTR(query);
   SNF_CHECK_ALIGN(query, 16);
   if (N < 0 || S <= 0) return SNF_E_ARG;
-  if (N == 0) return 0;
   make_query_kernel<<<(unsigned)ceil_div64(N * S, 256), 256, 0, (cudaStream_t)stream>>>(
       rays_o, rays_d, z, times, N, S, reinterpret_cast<float4 *>(query));
   count_launch();

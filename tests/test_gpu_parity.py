@@ -210,6 +210,48 @@ def test_composite_dt_backward():
     assert ((g_la.cpu() - la.grad).abs()[m] / la.grad.abs()[m]).max() <= 1e-3
 
 
+def test_ray_kernels_ragged_and_empty_batches():
+    """Edge shapes of the HBM-class kernels: no rays, one ray, a ragged warp (33 rays), sample counts that are not a
+    multiple of the warp size (50, 100) - against the oracle on the same seeded inputs."""
+    import sunerf_b200 as s
+    g = golden('sampling.npz')
+    D, R = float(g['distance']), float(g['solar_R'])
+    gen = torch.Generator().manual_seed(11)
+    for N, S in ((0, 64), (1, 64), (33, 50), (33, 100), (5, 192)):
+        b = s.rays.synthetic_rays(max(N, 1), seed=3)
+        ro, rd = b['rays_o'][:N], b['rays_d'][:N]
+        t_vals = torch.linspace(0., 1., S)
+        t_rand = torch.rand(N, S, generator=gen)
+        z, pts = s.ops.stratified_sample(ro.cuda(), rd.cuda(), t_vals.cuda(), t_rand.cuda(), D, R, want_points=True)
+        ref = orc.stratified_sample(ro, rd, t_vals[None], t_rand, torch.tensor(D), torch.tensor(R))
+        _exact(z, ref['z_vals'].numpy())
+        _exact(pts, ref['points'].numpy())
+        raw = torch.randn(N, S, 2, generator=gen) * 0.5
+        img, w, ab = s.ops.composite_emission_fwd(raw.cuda(), z, rd.cuda())
+        cref = orc.composite_emission(raw, z.cpu(), rd)
+        assert img.shape == (N, 1) and w.shape == (N, S)
+        if N:
+            assert rel_err(img, cref['image']) <= INT_TOL_F32
+            assert (w.cpu() - cref['weights']).abs().max() <= 1e-6
+            assert (ab.cpu() - cref['regularizing_quantity']).abs().max() <= 1e-6
+        gi = torch.rand(N, generator=gen)
+        g_raw = s.ops.composite_emission_bwd(raw.cuda(), z, rd.cuda(), gi.cuda(), None)
+        rr = raw.clone().requires_grad_()
+        (orc.composite_emission(rr, z.cpu(), rd)['image'][:, 0] * gi).sum().backward()
+        assert g_raw.shape == (N, S, 2)
+        if N:
+            assert (g_raw.cpu() - rr.grad).norm() <= 1e-4 * rr.grad.norm()
+        if S == 64:   # the resampler's 64 -> +128 shape
+            u = torch.linspace(0., 1., 128)
+            new_z, z_comb, inds, _ = s.ops.hier_resample(z, w, u.cuda(), want_inds=True)
+            assert new_z.shape == (N, 128) and z_comb.shape == (N, 192)
+            if N:
+                zc = z_comb.cpu()
+                assert bool((zc[:, 1:] >= zc[:, :-1]).all())
+                href = orc.hier_resample(ro, rd, z.cpu(), w.cpu())
+                assert (zc - href['z_vals']).abs().max() <= 1e-4
+
+
 # ------------------------------------------------------------------------------------------ a10 + drop-in forward
 def _emission_module(precision='fp32'):
     import sunerf_b200 as s
