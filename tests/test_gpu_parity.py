@@ -217,7 +217,9 @@ def test_ray_kernels_ragged_and_empty_batches():
     g = golden('sampling.npz')
     D, R = float(g['distance']), float(g['solar_R'])
     gen = torch.Generator().manual_seed(11)
-    for N, S in ((0, 64), (1, 64), (33, 50), (33, 100), (5, 192)):
+    a = golden('aia_response.npz')
+    tx, ty = torch.from_numpy(a['logT']), torch.from_numpy(a['table'])
+    for N, S in ((0, 64), (1, 64), (33, 50), (33, 100), (5, 192), (3, 256), (2, 3)):
         b = s.rays.synthetic_rays(max(N, 1), seed=3)
         ro, rd = b['rays_o'][:N], b['rays_d'][:N]
         t_vals = torch.linspace(0., 1., S)
@@ -241,6 +243,24 @@ def test_ray_kernels_ragged_and_empty_batches():
         assert g_raw.shape == (N, S, 2)
         if N:
             assert (g_raw.cpu() - rr.grad).norm() <= 1e-4 * rr.grad.norm()
+        # density-temperature head on the same shapes: 7 channels, some absent, optical depth O(1)
+        inf = torch.stack([torch.rand(N, S, generator=gen) * 2 - 0.3, 5.5 + torch.rand(N, S, generator=gen) * 1.6], -1)
+        wl = torch.tensor([94., 131., 171., 193., 211., 304., 335.]).repeat(N, 1)
+        wl[1::2, 2] = 0.
+        la = torch.rand(7, generator=gen) * 2 - 0.4
+        zs = torch.sort(z.cpu(), -1)[0]
+        img, w, q = s.ops.composite_dt_fwd(inf.cuda(), zs.cuda(), wl.cuda(), la.cuda(), torch.ones(1).cuda(), tx.cuda(), ty.cuda(), 1e17)
+        ii = inf.clone().requires_grad_()
+        dref = orc.composite_dt(ii, zs, wl, la, torch.tensor(1.0), tx, ty, 1e17)
+        gi7 = torch.rand(N, 7, generator=gen)
+        g_inf, g_la, g_vc = s.ops.composite_dt_bwd(inf.cuda(), zs.cuda(), wl.cuda(), la.cuda(), torch.ones(1).cuda(), tx.cuda(),
+                                                   ty.cuda(), 1e17, gi7.cuda(), None)
+        assert img.shape == (N, 7) and g_inf.shape == (N, S, 2)
+        if N:
+            ref = dref['image'].detach()
+            assert ((img.cpu() - ref).abs() <= INT_TOL_F32 * ref.abs() + 1e-30).all(), rel_err(img, ref, 1e-30)
+            (dref['image'] * gi7).sum().backward()
+            assert (g_inf.cpu() - ii.grad).norm() <= 1e-4 * ii.grad.norm()
         if S == 64:   # the resampler's 64 -> +128 shape
             u = torch.linspace(0., 1., 128)
             new_z, z_comb, inds, _ = s.ops.hier_resample(z, w, u.cuda(), want_inds=True)
