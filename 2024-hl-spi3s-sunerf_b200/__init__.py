@@ -10,6 +10,7 @@ Drop-in surface (same names, constructor arguments, forward contracts and state_
     sunerf/train/scaling.py          -> sunerf_b200.trainer    ImageAsinhScaling
     Lightning training_step + optim  -> sunerf_b200.trainer    RayTrainer (ray-sharded, one NCCL all-reduce/step)
     sunerf/evaluation/loader.py      -> sunerf_b200.image_render  ObserverRenderer.render_observer_image (rays on device)
+    (whole forward / backward chain as one C call each: sunerf_b200.fused.FusedRender over snf_render_fused_{fwd,bwd})
 
 The directory is named after the upstream repo (`2024-hl-spi3s-sunerf_b200`, not a valid Python identifier);
 `import sunerf_b200` resolves to it through the small alias package at the repo root.
@@ -24,7 +25,8 @@ from .trainer import RayTrainer, ImageAsinhScaling
 from . import rays, parallel, image_render, checkpoint, ray_store
 from .ray_store import RayStore
 from .image_render import ObserverRenderer
+from .fused import FusedRender
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
            'StratifiedSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
-           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore']
+           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore', 'FusedRender']

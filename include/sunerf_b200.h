@@ -137,6 +137,49 @@ int snf_adam_step_sched(float *params, const float *grads, float *exp_avg, float
                         float beta1, float beta2, float eps, float clip_norm, float grad_scale, float *scratch,
                         float *norm_out, void *stream);
 
+/* ---- whole chain: SuNeRFRendering.forward, sunerf/rendering/base_tracing.py:46-111, as ONE call ------------------
+ * (stratified sampling -> query -> coarse field -> compositing -> hierarchical resampling -> query -> fine field ->
+ * compositing -> epilogue), and its backward into the parameter gradients.  This is the entry a non-Python host binds;
+ * the Python classes launch the same kernels stage by stage.  Everything the descriptor points to is DEVICE memory except
+ * the W_x / B_x arrays themselves (HOST arrays of n_hidden+1 device pointers, as in snf_mlp_fwd_f32). */
+typedef struct snf_render_desc {
+  int kind;                 /* 0: EmissionRadiativeTransfer (emission.py:14-54), 1: DensityTemperatureRadiativeTransfer */
+  int mode;                 /* 0: fp32 field networks (W_x / B_x), 1: bf16 tensor cores (packed_x from snf_mlp_pack_bf16) */
+  int n_hidden, d_filter;   /* 8, 512 */
+  const float *const *W_coarse, *const *B_coarse, *const *W_fine, *const *B_fine;
+  const void *packed_coarse, *packed_fine;
+  float out_offset0, out_offset1;   /* NeRF_DT base_log_density / base_log_temperature (model.py:180-181), else 0 */
+  const float *t_vals;      /* [S]     StratifiedSampler buffer linspace(0,1,S), sampling.py:64 */
+  const float *u;           /* [n_new] HierarchicalSampler linspace(0,1,n_new), sampling.py:141 */
+  int S, n_new;             /* 64, 128; S + n_new <= 256 */
+  float distance, solar_R;  /* sampling.py:62-63 */
+  float reg_radius;         /* 1.2 / Rs_per_ds (base_tracing.py:43) or 1.25 / Rs_per_ds (density_temperature.py:273) */
+  int C;                    /* kind 1: wavelength channels per ray (<= 8) */
+  float pixel_intensity_factor;
+  const float *log_abs_coarse, *vol_c_coarse, *log_abs_fine, *vol_c_fine;   /* kind 1: [7], [1] per model */
+  const float *table_x, *table_y;                                           /* kind 1: [101], [7,101] */
+} snf_render_desc;
+
+int64_t snf_render_ws_bytes(const snf_render_desc *desc, int64_t N, int train);
+/* times[N], wavelengths[N,C] (kind 1, else NULL), t_rand[N,S] or NULL (perturb=False).  ws: 1024-byte aligned workspace.
+ * Outputs are the keys of the reference's output dict: z_vals_stratified[N,S] (may be NULL), coarse_image[N,C],
+ * z_vals_hierarchical[N,n_new], fine_image[N,C], height_map[N], absorption_map[N], regularization[N,S+n_new]
+ * (C = 1 for kind 0).  train != 0 keeps in ws what snf_render_fused_bwd needs, including
+ * d(reg_grad_scale * sum(regularization)) / d(regularizing_quantity) of the fine pass. */
+int snf_render_fused_fwd(const snf_render_desc *desc, const float *rays_o, const float *rays_d, const float *times,
+                         const float *wavelengths, const float *t_rand, int64_t N, void *ws, int train,
+                         float reg_grad_scale, float *z_vals_stratified, float *coarse_image,
+                         float *z_vals_hierarchical, float *fine_image, float *height_map, float *absorption_map,
+                         float *regularization, void *stream);
+/* Backward of the call above (same desc, N and ws): g_coarse_image / g_fine_image [N,C] are dL/d(image) of the two
+ * passes; with_reg_grad != 0 adds the regulariser term stored by the forward.  gW_x / gB_x: HOST arrays of device
+ * pointers, OVERWRITTEN with the gradients; g_log_abs_x[7] / g_vol_c_x[1] (kind 1) are ACCUMULATED into. */
+int snf_render_fused_bwd(const snf_render_desc *desc, const float *rays_d, const float *wavelengths, int64_t N, void *ws,
+                         const float *g_coarse_image, const float *g_fine_image, int with_reg_grad,
+                         float *const *gW_coarse, float *const *gB_coarse, float *const *gW_fine, float *const *gB_fine,
+                         float *g_log_abs_coarse, float *g_vol_c_coarse, float *g_log_abs_fine, float *g_vol_c_fine,
+                         void *stream);
+
 /* Measurement aid (bench.py): per-kernel CUDA-event timing of snf_mlp_bwd_bf16 on its launch stream.
  * snf_debug_time_backward(1) arms it and clears the sums, snf_debug_backward_ms(out[3]) returns the number of timed calls
  * and the summed milliseconds of {dgrad chain, wgrad, output-layer gradient}.  Off by default. */

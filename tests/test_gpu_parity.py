@@ -539,6 +539,72 @@ def test_ray_trainer_cuda_graph_replay_matches_eager():
     tb.check_finite()
 
 
+# ------------------------------------------------------------------------------------------ whole chain, one C call
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_fused_render_c_entry_matches_the_staged_path_emission(precision):
+    """snf_render_fused_fwd / _bwd (one C call per direction, what a non-Python host binds) against the Python classes that
+    launch the same kernels stage by stage: outputs bit-identical, parameter gradients equal up to the summation order of
+    the atomics."""
+    import sunerf_b200 as s
+    g, r = _emission_module(precision)
+    N = g['rays_o'].shape[0]
+    ro, rd, tm, tr = t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['t_rand'])
+    out = r(ro, rd, tm, t_rand=tr)
+    gc = torch.rand(N, 1, generator=torch.Generator().manual_seed(1)).cuda()
+    gf = torch.rand(N, 1, generator=torch.Generator().manual_seed(2)).cuda()
+    scale = 0.37 / (N * 192)
+    ((out['coarse_image'] * gc).sum() + (out['fine_image'] * gf).sum() + scale * out['regularization'].sum()).backward()
+    fr = s.FusedRender(r, N, train=True)
+    fo = fr.forward(ro, rd, tm, t_rand=tr, reg_grad_scale=scale)
+    for k in ('z_vals_stratified', 'coarse_image', 'z_vals_hierarchical', 'fine_image', 'height_map', 'absorption_map',
+              'regularization'):
+        _exact(fo[k], out[k].detach().cpu().numpy())
+    grads = fr.backward(gc, gf)
+    tol = 1e-5 if precision == 'fp32' else 1e-4
+    for name, model in (('coarse_model', r.coarse_model), ('fine_model', r.fine_model)):
+        ps = model.linear_params()
+        for got, p in zip(grads[name]['W'], ps[0::2]):
+            assert (got - p.grad).norm() <= tol * p.grad.norm(), name
+        for got, p in zip(grads[name]['B'], ps[1::2]):
+            assert (got - p.grad).norm() <= tol * p.grad.norm(), name
+    # forward-only instance: same images, nothing kept
+    with torch.no_grad():
+        fo2 = s.FusedRender(r, N).forward(ro, rd, tm, t_rand=tr)
+    _exact(fo2['fine_image'], fo['fine_image'].cpu().numpy())
+
+
+def test_fused_render_c_entry_matches_the_staged_path_density_temperature():
+    import sunerf_b200 as s
+    g, a, N = _dt_inputs()
+    torch.manual_seed(int(g['seed']))
+    r = s.DensityTemperatureRadiativeTransfer(Rs_per_ds=1, model=s.NeRF_DT, pixel_intensity_factor=1e17).cuda()
+    with torch.no_grad():
+        for i, c in enumerate(orc.AIA_CHANNELS):
+            r.coarse_model.log_absortpion[str(c)].fill_(float(g['log_abs_c'][i]) * 30)
+            r.fine_model.log_absortpion[str(c)].fill_(float(g['log_abs_f'][i]) * 30)
+    ro, rd, tm, wl, tr = t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['wavelengths']), t(g['t_rand'])
+    out = r(ro, rd, tm, wl, t_rand=tr)
+    C = wl.shape[1]
+    gc = torch.rand(N, C, generator=torch.Generator().manual_seed(1)).cuda()
+    gf = torch.rand(N, C, generator=torch.Generator().manual_seed(2)).cuda()
+    scale = 0.5 / (N * 192)
+    ((out['coarse_image'] * gc).sum() + (out['fine_image'] * gf).sum() + scale * out['regularization'].sum()).backward()
+    fr = s.FusedRender(r, N, train=True)
+    fo = fr.forward(ro, rd, tm, wl, t_rand=tr, reg_grad_scale=scale)
+    for k in ('z_vals_stratified', 'coarse_image', 'z_vals_hierarchical', 'fine_image', 'height_map', 'absorption_map',
+              'regularization'):
+        _exact(fo[k], out[k].detach().cpu().numpy())
+    grads = fr.backward(gc, gf)
+    for name, model in (('coarse_model', r.coarse_model), ('fine_model', r.fine_model)):
+        ps = model.linear_params()
+        for got, p in zip(grads[name]['W'] + grads[name]['B'], ps[0::2] + ps[1::2]):
+            assert (got - p.grad).norm() <= 1e-5 * p.grad.norm() + 1e-30, name
+        la = torch.stack([model.log_absortpion[str(c)].grad for c in orc.AIA_CHANNELS])
+        assert (grads[name]['log_abs'] - la).norm() <= 1e-4 * la.norm() + 1e-30
+        vc = model.volumetric_constant.grad.reshape(1)
+        assert (grads[name]['vol_c'] - vc).abs().max() <= 1e-4 * vc.abs().max()
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_emission_1024_rays():
     """BASELINE config sizes (1024 rays, 64+192 samples): size-independent invariants instead of oracle runs."""
