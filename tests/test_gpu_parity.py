@@ -539,6 +539,28 @@ def test_ray_trainer_cuda_graph_replay_matches_eager():
     tb.check_finite()
 
 
+def test_render_is_reentrant_from_a_thread_pool():
+    """The reference renders image batches concurrently from a ThreadPoolExecutor (sunerf/evaluation/loader.py:226-229):
+    the drop-in must give each concurrent call the result of the same call made alone."""
+    from concurrent.futures import ThreadPoolExecutor
+    import sunerf_b200 as s
+    for precision in ('fp32', 'bf16'):
+        g, r = _emission_module(precision)
+        r.sampler.perturb = False
+        batches = [{k: v.cuda() for k, v in s.rays.synthetic_rays(257 + 64 * i, seed=20 + i).items()} for i in range(6)]
+
+        def render(b):
+            with torch.no_grad():
+                return r(b['rays_o'], b['rays_d'], b['times'])['fine_image']
+
+        alone = [render(b).cpu() for b in batches]
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            together = list(ex.map(render, batches * 3))
+        torch.cuda.synchronize()
+        for i, img in enumerate(together):
+            _exact(img, alone[i % len(batches)].numpy())
+
+
 # ------------------------------------------------------------------------------------------ whole chain, one C call
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_fused_render_c_entry_matches_the_staged_path_emission(precision):
