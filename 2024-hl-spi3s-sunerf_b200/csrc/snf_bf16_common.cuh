@@ -95,9 +95,12 @@ struct Bars {
   // TMA stores of the previous layer have finished reading the A image
   __device__ uint32_t wrote(int slot) const { return base + 8u * (2 * NSTAGE + 8 + slot); }
   __device__ uint32_t afree() const { return base + 8u * (2 * NSTAGE + 16); }
+  // acc1a: the MMAs of half 1 over k-slabs 0..3 are complete (multicast commit): no instruction of this layer reads slabs
+  // 0..3 of the A image any more, half 0 of the next operand may be written while half 1 is still being accumulated
+  __device__ uint32_t acc1a() const { return base + 8u * (2 * NSTAGE + 17); }
 };
 constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
-static_assert(8 * (2 * NSTAGE + 17) <= 512, "barrier block");
+static_assert(8 * (2 * NSTAGE + 18) <= 512, "barrier block");
 }  // namespace fw
 
 // saved-image workspace (training): [enc][H = sin(pre)][D = dL/dpre] as [tile][layer][128 KB] bf16 images and

@@ -136,6 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     for (int k = 0; k < 8; ++k) mbar_init(bar.wrote(k), N_EPI_WARPS);
     mbar_init(bar.afree(), 1);
+    mbar_init(bar.acc1a(), 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
@@ -216,6 +217,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 }
                 mma_commit_2cta(bar.empty(s), 3);         // frees the stage in both CTAs
                 if (ks == nslab - 1) mma_commit_2cta(bar.acc(h), 3);   // this half of the layer is accumulated, in both CTAs
+                if (h == 1 && ks == (nslab < 4 ? nslab : 4) - 1) mma_commit_2cta(bar.acc1a(), 3);   // slabs 0..3 of A are no longer read
               }
               __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -389,22 +391,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
             // every warp is past the previous layer: the other bias buffer is idle -> stage the next layer's bias
             const int ln = (l + 1) & (NH - 1);
             for (int i = et; i < D; i += N_EPI) bias_s[(ln & 1) * D + i] = __ldg(bias_all + ln * D + i);
-          } else if (!last || TRAIN) {
-            // all MMAs of layer l are complete: the A image may be overwritten with h_l, half 0 first (from registers)
-            if (TRAIN) wait_afree();                  // ... once the stores of h_{l-1} (or of the encoder image) have read it
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int c = 0; c < CHUNKS; ++c)
-                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
-                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
-                               held[(CPT / 2) * j + 4 * c + 3]);
-            fence_proxy_async_smem();
-            if (!last) {   // hand the slabs to the MMA issuer first: the stores below are off the critical path
-              tcgen05_fence_before();
-              arrive_ready(0);
-            }
-            if (TRAIN) arrive_wrote(0);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -452,6 +438,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
                 if (TRAIN) arrive_wrote(sl);              // h_l for the weight gradients
               }
             }
+          }
+          if (h == 0 && (!last || TRAIN)) {
+            // Half 0 of h_l goes into slabs 0..3 of the A image as soon as no MMA of layer l reads them any more - that is
+            // half-way through the accumulation of half 1 (acc1a), normally already past: the 64 KB of shared-memory
+            // stores and the hand-over to the issuer run under the remaining MMAs, and the next layer's first 16
+            // instructions queue up right behind this layer's last one.
+            mbar_wait(bar.acc1a(), ph);
+            if (TRAIN) wait_afree();                  // ... and once the stores of h_{l-1} (or of the encoder image) have read it
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < CHUNKS; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
+                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
+                               held[(CPT / 2) * j + 4 * c + 3]);
+            fence_proxy_async_smem();
+            if (!last) {   // hand the slabs to the MMA issuer first: the stores are off the critical path
+              tcgen05_fence_before();
+              arrive_ready(0);
+            }
+            if (TRAIN) arrive_wrote(0);
           }
         }
         ph ^= 1;

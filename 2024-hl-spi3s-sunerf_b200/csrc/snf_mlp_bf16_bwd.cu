@@ -78,6 +78,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     for (int k = 0; k < 5; ++k) mbar_init(bar.ready(k), 2 * N_EPI_WARPS);
     for (int k = 0; k < 8; ++k) mbar_init(bar.wrote(k), N_EPI_WARPS);
     mbar_init(bar.afree(), 1);
+    mbar_init(bar.acc1a(), 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * D; i += NTHREADS) wout_s[i] = __ldg(reinterpret_cast<const float *>(p.packed + PACK_WOUT_OFF) + i);
@@ -145,6 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
                 for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (ks | k4) != 0);
                 mma_commit_2cta(bar.empty(s), 3);
                 if (ks == 7) mma_commit_2cta(bar.acc(h), 3);
+                if (h == 1 && ks == 3) mma_commit_2cta(bar.acc1a(), 3);   // slabs 0..3 of A are no longer read
               }
               __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -278,18 +280,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
           tcgen05_fence_after();
           uint32_t accA[16], accB[16];                // 16-column TMEM loads, double buffered
           tmem_ld16(tm_row + h * 256, accA);
-          if (h == 1) {
-            // all MMAs of layer l are complete: the A image may be overwritten with dpre_{l-1}, half 0 from registers
-            wait_afree();                             // ... once the stores of dpre_l have read it
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int c = 0; c < CHUNKS; ++c)
-                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
-                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
-                               held[(CPT / 2) * j + 4 * c + 3]);
-            publish(0, last ? -1 : 0);
-          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int sl = h * 4 + j;
@@ -329,6 +319,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
               publish(sl, last ? -1 : 1 + j);
             }
+          }
+          if (h == 0) {
+            // half 0 of dpre_{l-1} goes into slabs 0..3 of the A image as soon as no MMA of layer l reads them any more
+            // (acc1a: half-way through the accumulation of half 1) - see the forward kernel
+            mbar_wait(bar.acc1a(), ph);
+            wait_afree();                             // ... and once the stores of dpre_l have read it
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < CHUNKS; ++c)
+                *reinterpret_cast<uint4 *>(gA + j * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) =
+                    make_uint4(held[(CPT / 2) * j + 4 * c], held[(CPT / 2) * j + 4 * c + 1], held[(CPT / 2) * j + 4 * c + 2],
+                               held[(CPT / 2) * j + 4 * c + 3]);
+            publish(0, last ? -1 : 0);
           }
         }
         ph ^= 1;
