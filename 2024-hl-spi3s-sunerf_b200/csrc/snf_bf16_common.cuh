@@ -36,14 +36,16 @@ constexpr int BIAS_BYTES = D * 4;
 
 constexpr int FWD_BLOCKS = 2 * 2 + 7 * 16;   // forward weight blocks: layer 0 (2 n-halves x 2 k-slabs) + 7 x (2 x 8)
 constexpr int WT_BLOCKS = 7 * 16;            // W^T blocks for the dgrad chain (layers 1..7)
-// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB]
+// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB] |
+//                [FWD_BLOCKS x 32 KB in the order of the TS inference kernel (snf_mlp_bf16_ts.cu)]
 constexpr int64_t PACK_W_BYTES = (int64_t)FWD_BLOCKS * WBLK_BYTES;
 constexpr int64_t PACK_BIAS_OFF = PACK_W_BYTES;
 constexpr int64_t PACK_WOUT_OFF = PACK_BIAS_OFF + NH * D * 4;
 constexpr int64_t PACK_BOUT_OFF = PACK_WOUT_OFF + 2 * D * 4;
 constexpr int WOUT_BYTES = 2 * D * 4;        // 4 KB, rides through the weight ring as a pseudo-block
 constexpr int64_t PACK_WT_OFF = (PACK_BOUT_OFF + 16 + 1023) / 1024 * 1024;
-constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+constexpr int64_t PACK_TS_OFF = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;   // forward stages in TS-kernel order
+constexpr int64_t PACK_TOTAL_BYTES = PACK_TS_OFF + (int64_t)FWD_BLOCKS * WBLK_BYTES;
 
 
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }

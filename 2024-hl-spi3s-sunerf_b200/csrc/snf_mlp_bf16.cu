@@ -498,6 +498,9 @@ using namespace snf;
 
 // snf_mlp_bf16_bwd.cu
 int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st);
+int snf_bf16_pack_ts(const float *const *W, void *packed, cudaStream_t st);   // snf_mlp_bf16_ts.cu
+int snf_bf16_forward_ts(const float *x, int64_t M, const void *packed, float off0, float off1, float *out, int num_sms,
+                        cudaStream_t st);
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
                       float *const *gB, int num_sms, cudaStream_t st);
 
@@ -515,6 +518,10 @@ extern "C" int snf_debug_trace(long long *host) {
 }
 #endif
 
+// inference forward variant: 0 = activation operand in shared memory (SS), 1 = in tensor memory (TS, snf_mlp_bf16_ts.cu)
+static int g_fwd_variant = 0;
+extern "C" int snf_debug_fwd_variant(int v) { const int old = g_fwd_variant; if (v == 0 || v == 1) g_fwd_variant = v; return old; }
+
 extern "C" int64_t snf_mlp_pack_bytes(void) { return bf::PACK_TOTAL_BYTES; }
 
 extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, void *packed, void *stream) {
@@ -528,6 +535,8 @@ extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, v
   bf::pack_small_kernel<<<(nsmall + 255) / 256, 256, 0, st>>>(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], W[8], B[8],
                                                              reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_BIAS_OFF));
   count_launch(2);
+  if (g_fwd_variant == 1)   // forward stages in the order of the TS inference kernel (only when that variant is selected)
+    if (int e = snf_bf16_pack_ts(W, packed, st)) return e;
   return snf_bf16_pack_wt(W, packed, st);   // W^T blocks for the dgrad chain
 }
 
@@ -549,6 +558,7 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8); SNF_CHECK_ALIGN(packed, 1024);
   if (M < 0) return SNF_E_ARG;
   if (train) { SNF_CHECK_PTR(ws); SNF_CHECK_ALIGN(ws, 1024); }
+  if (!train && g_fwd_variant == 1) return snf_bf16_forward_ts(x, M, packed, off0, off1, out, num_sms(), (cudaStream_t)stream);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);

@@ -112,7 +112,8 @@ class NeRF(nn.Module):
         return 0.0, 0.0
 
     def _packed_ptr(self, weights, biases):
-        key = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+        # the TS inference variant reads its own stage order, packed only while it is selected
+        key = (ops.fwd_variant(),) + tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
         if self._pack is None or self._pack[0].device != weights[0].device:
             self._pack = ops.alloc_packed(weights[0].device)
             self._pack_key = None

@@ -184,6 +184,9 @@ int snf_render_fused_bwd(const snf_render_desc *desc, const float *rays_d, const
  * snf_debug_time_backward(1) arms it and clears the sums, snf_debug_backward_ms(out[3]) returns the number of timed calls
  * and the summed milliseconds of {dgrad chain, wgrad, output-layer gradient}.  Off by default. */
 int snf_debug_time_backward(int on);
+/* Selects the kernel behind snf_mlp_fwd_bf16(train = 0): 0 = activation operand in shared memory, 1 = in tensor memory
+ * (tcgen05 TS form).  Returns the previous value; any other argument only queries. */
+int snf_debug_fwd_variant(int variant);
 int snf_debug_backward_ms(double *out_ms);
 
 #ifdef __cplusplus

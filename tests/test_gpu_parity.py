@@ -117,6 +117,29 @@ def test_field_network_ragged_and_empty():
             assert net(torch.zeros(0, 4).cuda())['inferences'].shape == (0, 2)
 
 
+def test_field_network_forward_tmem_operand_variant():
+    """The alternative inference kernel with the activation operand in tensor memory (snf_debug_fwd_variant(1)): same
+    accumulation order as the default kernel, so the two agree to the summation order of the output layer."""
+    import sunerf_b200 as s
+    net, _ = _nets(3)
+    net.cuda()
+    net.precision = 'bf16'
+    ref = oracle_params(net)
+    try:
+        for M in (1, 127, 300, 4096):
+            x = torch.randn(M, 4, generator=torch.Generator().manual_seed(M))
+            s.ops.fwd_variant(0)
+            with torch.no_grad():
+                y_ss = net(x.cuda())['inferences'].cpu()
+            s.ops.fwd_variant(1)
+            with torch.no_grad():
+                y_ts = net(x.cuda())['inferences'].cpu()
+            assert (y_ts - y_ss).abs().max() <= 1e-6
+            assert (y_ts - orc.field_mlp(x, ref)).abs().max() <= INT_TOL_BF16
+    finally:
+        s.ops.fwd_variant(0)
+
+
 def test_simple_star():
     import sunerf_b200 as s
     g = golden('field.npz')

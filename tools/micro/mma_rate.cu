@@ -11,7 +11,7 @@ using namespace snf::tc;
 
 constexpr int A_IMG = 2 * 128 * 128, B_IMG = 2 * 128 * 128;   // K = 128: 2 k-slabs of 128 rows x 128 B
 
-struct Args { long long *cycles; int n, use_ts, reps; };
+struct Args { long long *cycles; int n, use_ts, reps, stage_sync; };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate_kernel(Args p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -21,7 +21,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate_kernel(
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (A_IMG + B_IMG) / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
   fence_proxy_async_smem();
-  if (tid == 0) { mbar_init(sBar, 1); mbar_init(sBar + 8, 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(sBar, 1); mbar_init(sBar + 8, 1); mbar_init(sBar + 32, 1); mbar_init(sBar + 40, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc_2cta(sSlot, 512);
   tcgen05_fence_before();
   cluster_sync_all();
@@ -53,7 +53,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate_kernel(
     }
     const uint32_t d = tmem;   // one accumulator, as in a real K loop
     const long long t0 = clock64();
-    if (p.use_ts) {
+    if (p.stage_sync) {
+      // what a real issuer does around every 8 instructions: wait for the weight stage (here: a barrier that is already
+      // complete), fence, issue, commit the stage's "empty" barrier
+      mbar_arrive(sBar + 32);                    // phase 0 of the dummy "full" barrier completes once and stays complete
+#pragma unroll 1
+      for (int r = 0; r < p.reps; ++r) {
+        mbar_wait(sBar + 32, 0);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_ts_2cta(d, at[j], bd[j], idesc, 1);
+        mma_commit_2cta(sBar + 40, 1);
+      }
+    } else if (p.use_ts) {
 #pragma unroll 1
       for (int r = 0; r < p.reps; ++r) {
 #pragma unroll
@@ -83,9 +95,9 @@ int main() {
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long *dc;
   cudaMalloc(&dc, sizeof(long long) * grid);
-  for (int use_ts = 0; use_ts < 2; ++use_ts)
+  for (int use_ts = 0; use_ts < 3; ++use_ts)
     for (int n : {256, 128, 64}) {
-      Args p{dc, n, use_ts, reps};
+      Args p{dc, n, use_ts > 0, reps, use_ts == 2};
       for (int it = 0; it < 2; ++it) {
         rate_kernel<<<grid, 128, smem>>>(p);
         cudaError_t e = cudaDeviceSynchronize();
@@ -98,7 +110,7 @@ int main() {
       mean /= c.size();
       const double per = mean / (reps * 8.0);
       const double flop_clk_sm = 2.0 * 256 * n * 16 / per / 2;
-      printf("%s N=%3d: %.1f cycles per MMA, %.0f flop/clk/SM (%.0f %% of 8192)\n", use_ts ? "A from TMEM  " : "A from shared", n, per,
+      printf("%s N=%3d: %.1f cycles per MMA, %.0f flop/clk/SM (%.0f %% of 8192)\n", use_ts == 2 ? "TMEM + stage sync" : use_ts ? "A from TMEM  " : "A from shared", n, per,
              flop_clk_sm, 100.0 * flop_clk_sm / 8192);
     }
   return 0;
