@@ -2,22 +2,24 @@
 // ONE persistent, warp-specialised kernel per pass.  Replaces PositionalEncoding.forward / NeRF.forward /
 // NeRF_DT.forward (sunerf/model/model.py:123-132, 44-57, 169-187) in "bf16-MLP mode" (BASELINE.json: 1e-2).
 //
-// One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 points, 384 threads per CTA; the activations
-// never leave the SM between layers:
+// One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 points, 640 threads per CTA; the activations never
+// leave the SM between layers:
 //   warp 0      TMA producer : streams this CTA's half (128 output features, 16 KB) of every pre-packed bf16 weight
 //                              block (UMMA K-major SWIZZLE_128B image, L2 evict_last) through a 5-stage mbarrier ring
 //   warp 1      MMA issuer   : leader CTA: tcgen05.mma M=256 (pair) x N=256 x K=16, A = activation image in shared
 //                              memory (128 KB), D = 128 x 512 fp32 = all of TMEM; peer CTA: relays "my half of the
 //                              stage has landed" to the leader with a relaxed remote mbarrier arrive
-//   warps 4-11  epilogue     : thread = (row, 32-column group).  A layer is accumulated as two temporal N-halves; the
-//                              epilogue of half 0 (TMEM -> +bias -> sin -> bf16) runs under the MMAs of half 1 and
-//                              keeps its result in registers until the A image may be overwritten, half 1 is written
-//                              slab by slab so the next layer's MMAs start k-slab by k-slab.
+//   warp 2      store warp   : (training) TMA-stores every finished slab of the A image for the backward
+//   warps 4-19  epilogue     : thread = (row, 16-column group).  A layer is accumulated as two temporal N-halves; the
+//                              epilogue of half 0 (TMEM -> +bias -> sin -> bf16) runs under the MMAs of half 1, keeps its
+//                              result in registers and writes it half-way through half 1 (acc1a: no MMA of the layer
+//                              reads slabs 0-3 any more); half 1 is written slab by slab, so the next layer's MMAs queue
+//                              up behind this layer's last one and continue k-slab by k-slab.
 //                              Layer 0's A image is the sin/cos encoding computed in place; the 512->2 output layer
 //                              is a register dot product fused into the last epilogue.
-//   setmaxnreg  40 registers for the control warpgroup, 232 for the two epilogue warpgroups.
-// Training mode additionally writes, per layer, the activation image h = sin(pre) (TMA bulk stores straight from the
-// A image, 4 KB per warp pair) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
+//   setmaxnreg  40 registers for the control warpgroup, 104 for the four epilogue warpgroups.
+// Training mode additionally writes, per layer, the activation image h = sin(pre) (16 KB TMA bulk stores straight from the
+// A image, issued by the store warp) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
 // 16 epilogue warps (4 per SM sub-partition) hide the MUFU / TMEM-load latencies of the sine epilogue better than 8:
 // measured -7 % on the forward; the dgrad epilogue (no MUFU) is faster with 8 warps and more registers.
 #define SNF_EPI_GROUPS 4
