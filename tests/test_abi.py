@@ -61,3 +61,26 @@ def test_reference_surface():
     assert {'in_layer.0.freq_bands', 'in_layer.1.weight', 'layers.6.bias', 'out_layer.weight', 'log_absortpion.94',
             'log_absortpion.335', 'volumetric_constant'} <= keys
     assert sum(p.numel() for p in s.NeRF().parameters()) == 1883138
+
+
+def test_render_workspace_size_is_host_arithmetic():
+    """snf_render_ws_bytes / snf_mlp_ws_bytes need no GPU: sizes grow with the batch, a training forward keeps more than an
+    inference one, and a bad descriptor is an error code, not a crash."""
+    import sunerf_b200
+    from sunerf_b200 import _lib
+    L = _lib.lib()
+    d = _lib.RenderDesc()
+    d.kind, d.mode, d.n_hidden, d.d_filter = 0, 1, 8, 512
+    d.packed_coarse = d.packed_fine = 1024          # any non-null value: nothing is dereferenced
+    d.t_vals = d.u = 1024
+    d.S, d.n_new = 64, 128
+    small = L.snf_render_ws_bytes(ctypes.byref(d), 256, 0)
+    big = L.snf_render_ws_bytes(ctypes.byref(d), 1024, 0)
+    train = L.snf_render_ws_bytes(ctypes.byref(d), 1024, 1)
+    assert 0 < small < big < train
+    assert train >= L.snf_mlp_ws_bytes(1024 * 64, 8, 512, 1, 1) + L.snf_mlp_ws_bytes(1024 * 192, 8, 512, 1, 1)
+    d.S, d.n_new = 200, 128                          # S + n_new > 256: outside what the compositing kernels are built for
+    assert L.snf_render_ws_bytes(ctypes.byref(d), 256, 0) == -2
+    d.S, d.kind = 64, 7
+    assert L.snf_render_ws_bytes(ctypes.byref(d), 256, 0) == -1
+    assert L.snf_render_ws_bytes(None, 256, 0) == -1
