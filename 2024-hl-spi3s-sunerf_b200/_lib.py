@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(_PKG, 'lib')
 # SNF_LIB_NAME: developer-only, lets experiment builds (SNF_NVCC_EXTRA) live next to the product library
 LIB_PATH = os.path.join(LIB_DIR, os.environ.get('SNF_LIB_NAME', 'libsunerf_b200.so'))
 SOURCES = ['snf_sampling.cu', 'snf_rays.cu', 'snf_composite.cu', 'snf_mlp_f32.cu', 'snf_mlp_bf16.cu', 'snf_mlp_bf16_bwd.cu',
-           'snf_optim.cu', 'snf_render.cu', 'snf_mlp_bf16_ts.cu']
+           'snf_optim.cu', 'snf_render.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -93,7 +93,6 @@ _PROTOS = {
     'snf_adam_step_sched': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P, _P, _P]),
     'snf_debug_time_backward': (_I, [_I]),
     'snf_debug_backward_ms': (_I, [_P]),
-    'snf_debug_fwd_variant': (_I, [_I]),
     'snf_render_ws_bytes': (_L, [_P, _L, _I]),
     'snf_render_fused_fwd': (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     'snf_render_fused_bwd': (_I, [_P, _P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

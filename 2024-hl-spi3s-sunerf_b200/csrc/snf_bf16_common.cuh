@@ -1,4 +1,9 @@
-// Constants, layouts and role helpers shared by the bf16 tensor-core kernels (forward, dgrad chain, wgrad).
+// Constants, layouts and role helpers shared by the 16-bit tensor-core kernels (forward, dgrad chain, wgrad).
+// Operand format: fp16 for every MMA operand (weights, activations, dL/dpre), fp32 accumulation.  The path keeps the
+// name the task gives it ("bf16-MLP mode"); round 1 ran bf16 operands, whose 8-bit significand on the WEIGHTS alone costs
+// 5.7e-3 of per-parameter gradient accuracy against the 1e-3 gate (tools/micro/bf16_grad_study.py: fp16 weights 6.8e-4).
+// tcgen05 kind::f16 rejects A and B of different 16-bit formats (illegal instruction, tools/umma_probe.cu "mixed"), so the
+// back-propagated gradients are fp16 too, carried with one power-of-two scale per backward call (GradScale below).
 #pragma once
 #include "snf_common.cuh"
 #include "snf_tcgen05.cuh"
@@ -10,7 +15,7 @@ using namespace tc;
 constexpr int TILE_M = 128;                  // points per CTA tile (= TMEM lanes); a CTA pair covers 256
 constexpr int D = 512;                       // hidden width
 constexpr int NH = 8;                        // hidden layers
-constexpr int K0 = 96;                       // layer-0 K: 84 features + 4 bf16 residuals of x + 8 zero columns
+constexpr int K0 = 96;                       // layer-0 K: 84 features + 4 fp16 residuals of x + 8 zero columns
 constexpr int SLAB_BYTES = TILE_M * 128;     // one K-slab (64 bf16) of a 128-row image: 16 KB
 constexpr int A_BYTES = 8 * SLAB_BYTES;      // 128 KB activation image
 constexpr int C_BYTES = TILE_M * D;          // 64 KB: cos(pre) of one tile and layer as int8 (x 127), chunk-major:
@@ -36,37 +41,63 @@ constexpr int BIAS_BYTES = D * 4;
 
 constexpr int FWD_BLOCKS = 2 * 2 + 7 * 16;   // forward weight blocks: layer 0 (2 n-halves x 2 k-slabs) + 7 x (2 x 8)
 constexpr int WT_BLOCKS = 7 * 16;            // W^T blocks for the dgrad chain (layers 1..7)
-// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB] |
-//                [FWD_BLOCKS x 32 KB in the order of the TS inference kernel (snf_mlp_bf16_ts.cu)]
+// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB]
 constexpr int64_t PACK_W_BYTES = (int64_t)FWD_BLOCKS * WBLK_BYTES;
 constexpr int64_t PACK_BIAS_OFF = PACK_W_BYTES;
 constexpr int64_t PACK_WOUT_OFF = PACK_BIAS_OFF + NH * D * 4;
 constexpr int64_t PACK_BOUT_OFF = PACK_WOUT_OFF + 2 * D * 4;
 constexpr int WOUT_BYTES = 2 * D * 4;        // 4 KB, rides through the weight ring as a pseudo-block
 constexpr int64_t PACK_WT_OFF = (PACK_BOUT_OFF + 16 + 1023) / 1024 * 1024;
-constexpr int64_t PACK_TS_OFF = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;   // forward stages in TS-kernel order
-constexpr int64_t PACK_TOTAL_BYTES = PACK_TS_OFF + (int64_t)FWD_BLOCKS * WBLK_BYTES;
+constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+
+constexpr int FMT = FMT_F16;                 // operand format of every MMA of the field network
 
 
-__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float h_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xFFFFu))); }
+__device__ __forceinline__ float h_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 
-// cos(pre) travels from the forward to the dgrad chain as int8 = rint(127 cos): absolute error <= 1/254, about what
-// a bf16 pre-activation gave for |pre| ~ 2, at half the HBM bytes (the forward is bound by HBM writes).
-// Encode: 127 c + 1.5 * 2^23 leaves the two's-complement integer in the low mantissa byte.
+// cos(pre) travels from the forward to the dgrad chain as ONE byte: bit 7 = (cos < 0), bits 0..6 = q = rint(127 t) with
+// t = sqrt(1 - |cos|); decode |cos| = 1 - (q/127)^2.  The resolution is finest where the cosines pile up - next to +-1,
+// i.e. small pre-activations - and 2/254 at the zero crossings.  Round 1 stored rint(127 cos): every cosine above
+// 1 - 1/254 came back as exactly 1, a one-sided error that does not average out over points and cost 3.4e-3 of
+// per-parameter gradient accuracy by itself; this code costs 1.1e-4 (tools/micro/bf16_grad_study.py, 'i8half').
+// With the half-angle values s2 = sin(pre/2), c2 = cos(pre/2) the forward already holds: t = sqrt(2) min(|s2|, |c2|),
+// cos < 0 <=> |s2| > |c2|, and sin(pre) = 2 s2 c2 - two MUFU per element as before.
+// Encode: t' + 1.5 * 2^23 leaves the integer in the low mantissa byte.
 constexpr float COSQ_MAGIC = 12582912.f;
-__device__ __forceinline__ float cosq_enc(float v) { return fmaf(__cosf(v), 127.f, COSQ_MAGIC); }
-// (Measured twice, with 8 and with 16 epilogue warps: computing half of the cosines with an FMA-pipe polynomial instead of
-// MUFU.COS changes nothing - the training forward is bound by its HBM writes, 3.0 of the 3.9 TB/s a pure fill reaches.)
-__device__ __forceinline__ uint32_t cosq_pack4(float t0, float t1, float t2, float t3) {   // four encoded values -> 4 int8
-  return __byte_perm(__byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0040),
-                     __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0040), 0x5410);
+constexpr float COSQ_SCALE = 179.60512f;     // 127 sqrt(2)
+__device__ __forceinline__ uint32_t cosq_enc(float s2, float c2) {
+  const float as = fabsf(s2), ac = fabsf(c2);
+  const uint32_t q = __float_as_uint(fmaf(fminf(as, ac), COSQ_SCALE, COSQ_MAGIC));
+  return as > ac ? (q | 0x80u) : q;
 }
-// Decode byte b of w ^ 0x80808080 (offset binary): 2^23 + u as float bits; the subtraction is exact, so the only
-// rounding is the final scaling.
-__device__ __forceinline__ float cosq_get(uint32_t wx, int b) {
-  const uint32_t f = __byte_perm(wx, 0x4B000000u, 0x7650 + b);   // bytes: [wx.b, 0x00, 0x00, 0x4B]
-  return (__uint_as_float(f) - 8388736.f) * (1.f / 127.f);
+__device__ __forceinline__ uint32_t cosq_pack4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3) {   // low bytes -> 4 codes
+  return __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
+}
+// Decode codes 2 pr, 2 pr + 1 of the word w as a half2 (packed fp16 arithmetic: q <= 127 is exact, q^2 rounds at 2^-11
+// relative, far below the code's own step): halves 0x64qq = 1024 + q.
+template <int PR> __device__ __forceinline__ __half2 cosq_dec2(uint32_t w) {
+  const uint32_t hq = __byte_perm(w & 0x7F7F7F7Fu, 0x64646464u, PR == 0 ? 0x4140 : 0x4342);
+  const __half2 q = __hsub2(*reinterpret_cast<const __half2 *>(&hq), __float2half2_rn(1024.f));
+  const __half2 c = __hfma2(__hmul2(q, q), __float2half2_rn(-1.f / 16129.f), __float2half2_rn(1.f));
+  const uint32_t sg = __byte_perm(w, 0u, PR == 0 ? 0x1404 : 0x3424) & 0x80008000u;   // code bit 7 -> fp16 sign bit
+  const uint32_t cb = *reinterpret_cast<const uint32_t *>(&c) ^ sg;
+  return *reinterpret_cast<const __half2 *>(&cb);
+}
+
+// One power-of-two scale per backward call keeps the fp16 dL/dpre images in range: S = 2^-ceil(log2(bound)) with
+// bound = max_p max(|g0|, |g1|) * max_j (|W_out[0,j]| + |W_out[1,j]|) >= max |dL/dh_7|, so the first image peaks in
+// (0.5, 1] and the chain may grow 2^16-fold before it overflows; elements 2^-24 below the peak flush to zero (their
+// share of a gradient sum is below fp32 resolution).  The whole backward is linear in g, so the wgrad un-scales exactly
+// when it flushes its fp32 accumulators.  ws.scale = {absmax bits of g (uint), S, 1/S, pad}.
+struct GradScale { uint32_t gmax_bits; float S, invS, pad; };
+__device__ __forceinline__ float grad_scale_from(float gmax, float wmax) {
+  const float bound = gmax * wmax;
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;            // all-zero, Inf or NaN gradients: nothing to protect
+  int e;
+  frexpf(bound, &e);                                               // bound = m 2^e, m in [0.5, 1)
+  e = e > 126 ? 126 : e < -126 ? -126 : e;
+  return ldexpf(1.f, -e);
 }
 
 // ---- layer-chain kernels (forward, dgrad chain): shared-memory layout and barrier block
@@ -105,11 +136,12 @@ constexpr int TMEM_SLOT_OFF = OFF_BAR + 8 * (2 * NSTAGE + 7);
 static_assert(8 * (2 * NSTAGE + 18) <= 512, "barrier block");
 }  // namespace fw
 
-// saved-image workspace (training): [enc][H = sin(pre)][D = dL/dpre] as [tile][layer][128 KB] bf16 images and
-// [C = cos(pre)] as [tile][layer][64 KB] int8.
+// saved-image workspace (training): [enc][H = sin(pre)][D = S dL/dpre] as [tile][layer][128 KB] fp16 images,
+// [C = cos(pre)] as [tile][layer][64 KB] one-byte codes, and the GradScale block of the backward.
 // Sized for an even number of tiles (CTA pairs always process two).
 struct Bf16Ws {
   uint8_t *enc, *h, *pre, *d;
+  GradScale *scale;
   int64_t bytes;
 };
 inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
@@ -123,6 +155,7 @@ inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
     w.h = p + off; off += tiles * NH * (int64_t)A_BYTES;
     w.pre = p + off; off += tiles * NH * (int64_t)C_BYTES;   // quantised cos(pre), see C_BYTES
     w.d = p + off; off += tiles * NH * (int64_t)A_BYTES;
+    w.scale = reinterpret_cast<GradScale *>(p + off); off += 256;
   }
   w.bytes = off > 0 ? off : 256;
   return w;

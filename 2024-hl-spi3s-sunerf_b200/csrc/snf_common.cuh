@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "../../include/sunerf_b200.h"
 
 namespace snf {
@@ -12,6 +13,16 @@ constexpr unsigned kFull = 0xffffffffu;
 // launch accounting for bench.py's gpu_launches
 extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+// per-device one-time state (snf_mlp_bf16.cu): the SM count and the opt-in shared-memory attributes of the kernels
+// belong to a device, and one process may drive several (nn.DataParallel-style rendering from a thread pool)
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  std::once_flag once;
+  int num_sms = 0;
+  int status = 0;
+};
+extern DeviceState g_devices[kMaxDevices];
 
 inline int launch_status() {
   cudaError_t e = cudaPeekAtLastError();
@@ -70,6 +81,12 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
   return v;
 }
+
+}  // namespace snf
+// one-time setup of the CURRENT device (thread-safe); returns 0 or an error code, optionally the SM count
+int snf_device_setup(int *num_sms_out);
+int snf_set_kernel_attributes();
+namespace snf {
 
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

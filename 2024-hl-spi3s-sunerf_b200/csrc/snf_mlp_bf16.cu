@@ -1,17 +1,18 @@
-// bf16 tensor-core field network for sm_100a: positional encoding + 8 x (Linear(512)+sin) + Linear(2) fused in
+// 16-bit tensor-core field network for sm_100a: positional encoding + 8 x (Linear(512)+sin) + Linear(2) fused in
 // ONE persistent, warp-specialised kernel per pass.  Replaces PositionalEncoding.forward / NeRF.forward /
 // NeRF_DT.forward (sunerf/model/model.py:123-132, 44-57, 169-187) in "bf16-MLP mode" (BASELINE.json: 1e-2).
+// Operands are fp16 (weights and activations; 11-bit significands, see snf_bf16_common.cuh), accumulation fp32.
 //
 // One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 points, 640 threads per CTA; the activations never
 // leave the SM between layers:
-//   warp 0      TMA producer : streams this CTA's half (128 output features, 16 KB) of every pre-packed bf16 weight
+//   warp 0      TMA producer : streams this CTA's half (128 output features, 16 KB) of every pre-packed fp16 weight
 //                              block (UMMA K-major SWIZZLE_128B image, L2 evict_last) through a 5-stage mbarrier ring
 //   warp 1      MMA issuer   : leader CTA: tcgen05.mma M=256 (pair) x N=256 x K=16, A = activation image in shared
 //                              memory (128 KB), D = 128 x 512 fp32 = all of TMEM; peer CTA: relays "my half of the
 //                              stage has landed" to the leader with a relaxed remote mbarrier arrive
 //   warp 2      store warp   : (training) TMA-stores every finished slab of the A image for the backward
 //   warps 4-19  epilogue     : thread = (row, 16-column group).  A layer is accumulated as two temporal N-halves; the
-//                              epilogue of half 0 (TMEM -> +bias -> sin -> bf16) runs under the MMAs of half 1, keeps its
+//                              epilogue of half 0 (TMEM -> +bias -> sin -> fp16) runs under the MMAs of half 1, keeps its
 //                              result in registers and writes it half-way through half 1 (acc1a: no MMA of the layer
 //                              reads slabs 0-3 any more); half 1 is written slab by slab, so the next layer's MMAs queue
 //                              up behind this layer's last one and continue k-slab by k-slab.
@@ -19,7 +20,7 @@
 //                              is a register dot product fused into the last epilogue.
 //   setmaxnreg  40 registers for the control warpgroup, 104 for the four epilogue warpgroups.
 // Training mode additionally writes, per layer, the activation image h = sin(pre) (16 KB TMA bulk stores straight from the
-// A image, issued by the store warp) and cos(pre) as int8 (coalesced 16 B stores, chunk-major layout) for the backward.
+// A image, issued by the store warp) and cos(pre) as one-byte codes (coalesced 16 B stores, chunk-major layout) for the backward.
 // 16 epilogue warps (4 per SM sub-partition) hide the MUFU / TMEM-load latencies of the sine epilogue better than 8:
 // measured -7 % on the forward; the dgrad epilogue (no MUFU) is faster with 8 warps and more registers.
 #define SNF_EPI_GROUPS 4
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, cons
     v[i] = x;
   }
   uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  o.x = pack_f16x2(v[0], v[1]); o.y = pack_f16x2(v[2], v[3]);
+  o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
   // (r>>3)*1024 + (r&7)*128 + pos*16 == r*128 + pos*16: the image is row-linear, only the chunk order is permuted
   dst[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
 }
@@ -88,9 +89,9 @@ struct FwdParams {
   const uint8_t *packed;  // PACK_TOTAL_BYTES
   float2 *out;            // [M]
   float off0, off1;
-  uint8_t *save_enc;      // train: [tiles][2 slabs][16 KB] bf16 image, else null
+  uint8_t *save_enc;      // train: [tiles][2 slabs][16 KB] fp16 image, else null
   uint8_t *save_h;        // train: [tiles][8][128 KB]   sin(pre)
-  uint8_t *save_pre;      // train: [tiles][8][64 KB]    cos(pre) as int8 (C_BYTES layout) for the dgrad chain
+  uint8_t *save_pre;      // train: [tiles][8][64 KB]    cos(pre) codes (C_BYTES layout, cosq_enc) for the dgrad chain
 };
 
 #ifndef SNF_TRACE_TRAIN
@@ -175,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
       // Layer l is accumulated as two temporal halves (D columns [0,256) then [256,512)); the first half of layer
       // l+1 starts as soon as the epilogue has produced its k-slabs, while it is still draining half 1 of layer l.
       // The whole warp runs the (uniform) control flow, one elected lane issues: descriptors stay in uniform registers.
-      const uint32_t idesc = idesc_bf16(256, NCHUNK);
+      const uint32_t idesc = idesc_f16kind(256, NCHUNK, FMT, FMT);
       const uint64_t adesc0 = smem_desc(sA, 16, 1024), bdesc0 = smem_desc(sW, 16, 1024);
       uint32_t rph = 0;
       PROF_DECL(t_ready); PROF_DECL(t_full); PROF_T0(t_begin);
@@ -328,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
 #endif
       // ---- layer-0 operand: positional encoding of this row, written straight into the A image (slabs 0, 1).
       //      The 10 frequencies are dealt round-robin to the column groups; group 0 adds the raw coordinates, the last
-      //      group the bf16 residual of x and the zero padding.
+      //      group the fp16 residual of x and the zero padding.
       {
         PROF_T0(t0);
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -339,13 +340,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         auto put8 = [&](int feat0, float a, float b, float c, float d) {   // 4 consecutive features (8 bytes)
           const int c8 = feat0 >> 3;
           *reinterpret_cast<uint2 *>(gA + (c8 >> 3) * SLAB_BYTES + sw128_chunk_off(row, c8 & 7) + (feat0 & 7) * 2) =
-              make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+              make_uint2(pack_f16x2(a, b), pack_f16x2(c, d));
         };
         if (g == 0) put8(0, xc[0], xc[1], xc[2], xc[3]);
         if (g == EPI_GROUPS - 1) {
           float rs[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) rs[c] = xc[c] - __bfloat162float(__float2bfloat16_rn(xc[c]));   // what bf16 drops from x
+          for (int c = 0; c < 4; ++c) rs[c] = xc[c] - __half2float(__float2half_rn(xc[c]));   // what fp16 drops from x
           put8(84, rs[0], rs[1], rs[2], rs[3]);
           put8(88, 0.f, 0.f, 0.f, 0.f);
           put8(92, 0.f, 0.f, 0.f, 0.f);
@@ -376,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
         const bool last = (l == NH - 1);
         const float *bl = bias_s + (l & 1) * D;
         uint8_t *psave = TRAIN ? p.save_pre + ((int64_t)tile * NH + l) * C_BYTES : nullptr;
-        uint32_t held[4 * CPT / 2];                   // half 0 of h_l (bf16 pairs): the MMAs of half 1 still read A
+        uint32_t held[4 * CPT / 2];                   // half 0 of h_l (fp16 pairs): the MMAs of half 1 still read A
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -408,9 +409,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_fwd
               const float4 b = *reinterpret_cast<const float4 *>(bl + col0 + i);
               const float v0 = __uint_as_float(cur[i]) + b.x, v1 = __uint_as_float(cur[i + 1]) + b.y;
               const float v2 = __uint_as_float(cur[i + 2]) + b.z, v3 = __uint_as_float(cur[i + 3]) + b.w;
-              const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
-              pk[i / 2] = pack_bf16x2(s0, s1); pk[i / 2 + 1] = pack_bf16x2(s2, s3);
-              if (TRAIN) cq[i / 4] = cosq_pack4(cosq_enc(v0), cosq_enc(v1), cosq_enc(v2), cosq_enc(v3));   // cos(pre) for the backward
+              float s0, s1, s2, s3;
+              if (TRAIN) {
+                // half-angle pair per element: sin(pre) = 2 s c, and the cosine code of the backward from min(|s|, |c|)
+                const float hs0 = __sinf(0.5f * v0), hc0 = __cosf(0.5f * v0), hs1 = __sinf(0.5f * v1), hc1 = __cosf(0.5f * v1);
+                const float hs2 = __sinf(0.5f * v2), hc2 = __cosf(0.5f * v2), hs3 = __sinf(0.5f * v3), hc3 = __cosf(0.5f * v3);
+                s0 = (hs0 + hs0) * hc0; s1 = (hs1 + hs1) * hc1; s2 = (hs2 + hs2) * hc2; s3 = (hs3 + hs3) * hc3;
+                cq[i / 4] = cosq_pack4(cosq_enc(hs0, hc0), cosq_enc(hs1, hc1), cosq_enc(hs2, hc2), cosq_enc(hs3, hc3));
+              } else {
+                s0 = __sinf(v0); s1 = __sinf(v1); s2 = __sinf(v2); s3 = __sinf(v3);
+              }
+              pk[i / 2] = pack_f16x2(s0, s1); pk[i / 2 + 1] = pack_f16x2(s2, s3);
               if (last) {   // fused output layer: out = W_out h + b_out
                 const float4 wa = *reinterpret_cast<const float4 *>(wout_s + col0 + i);
                 const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + col0 + i);
@@ -500,9 +509,6 @@ using namespace snf;
 
 // snf_mlp_bf16_bwd.cu
 int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st);
-int snf_bf16_pack_ts(const float *const *W, void *packed, cudaStream_t st);   // snf_mlp_bf16_ts.cu
-int snf_bf16_forward_ts(const float *x, int64_t M, const void *packed, float off0, float off1, float *out, int num_sms,
-                        cudaStream_t st);
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
                       float *const *gB, int num_sms, cudaStream_t st);
 
@@ -520,10 +526,6 @@ extern "C" int snf_debug_trace(long long *host) {
 }
 #endif
 
-// inference forward variant: 0 = activation operand in shared memory (SS), 1 = in tensor memory (TS, snf_mlp_bf16_ts.cu)
-static int g_fwd_variant = 0;
-extern "C" int snf_debug_fwd_variant(int v) { const int old = g_fwd_variant; if (v == 0 || v == 1) g_fwd_variant = v; return old; }
-
 extern "C" int64_t snf_mlp_pack_bytes(void) { return bf::PACK_TOTAL_BYTES; }
 
 extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, void *packed, void *stream) {
@@ -537,20 +539,37 @@ extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, v
   bf::pack_small_kernel<<<(nsmall + 255) / 256, 256, 0, st>>>(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], W[8], B[8],
                                                              reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_BIAS_OFF));
   count_launch(2);
-  if (g_fwd_variant == 1)   // forward stages in the order of the TS inference kernel (only when that variant is selected)
-    if (int e = snf_bf16_pack_ts(W, packed, st)) return e;
   return snf_bf16_pack_wt(W, packed, st);   // W^T blocks for the dgrad chain
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    g_num_sms = n > 0 ? n : 148;
-  }
-  return g_num_sms;
+// Per-DEVICE one-time setup (the reference renders through nn.DataParallel from a thread pool, evaluation/loader.py:
+// 37-39,143,226-229: several devices and several host threads in one process).  cudaFuncAttributeMaxDynamicSharedMemorySize
+// and the SM count belong to the current device, not to the process.
+int snf_device_setup(int *num_sms_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= snf::kMaxDevices) return SNF_E_ARG;
+  snf::DeviceState &d = snf::g_devices[dev];
+  std::call_once(d.once, [&]() {
+    int n = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    d.num_sms = (err == cudaSuccess && n > 0) ? n : 148;
+    d.status = snf_set_kernel_attributes();
+  });
+  if (num_sms_out) *num_sms_out = d.num_sms;
+  return d.status;
+}
+
+int snf_bf16_set_attributes_bwd();   // snf_mlp_bf16_bwd.cu
+int snf_sampling_set_attributes();   // snf_sampling.cu
+int snf_set_kernel_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  if (int r = snf_bf16_set_attributes_bwd()) return r;
+  return snf_sampling_set_attributes();
 }
 
 extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, float off0, float off1, float *out,
@@ -560,15 +579,8 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   SNF_CHECK_ALIGN(x, 16); SNF_CHECK_ALIGN(out, 8); SNF_CHECK_ALIGN(packed, 1024);
   if (M < 0) return SNF_E_ARG;
   if (train) { SNF_CHECK_PTR(ws); SNF_CHECK_ALIGN(ws, 1024); }
-  if (!train && g_fwd_variant == 1) return snf_bf16_forward_ts(x, M, packed, off0, off1, out, num_sms(), (cudaStream_t)stream);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  int nsm = 0;
+  if (int e = snf_device_setup(&nsm)) return e;
   bf::FwdParams p{};
   p.x = reinterpret_cast<const float4 *>(x);
   p.M = M;
@@ -581,7 +593,7 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
     bf::Bf16Ws w = bf::bf16_layout(ws, M, 1);
     p.save_enc = w.enc; p.save_h = w.h; p.save_pre = w.pre;
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
   grid &= ~1;   // whole CTA pairs
   if (train) bf::mlp_fwd_bf16_kernel<true><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   else bf::mlp_fwd_bf16_kernel<false><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, (cudaStream_t)stream>>>(p);
@@ -597,5 +609,7 @@ extern "C" int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, c
   if (M <= 0) return SNF_E_ARG;
   for (int l = 0; l <= bf::NH; ++l) { SNF_CHECK_PTR(gW[l]); SNF_CHECK_PTR(gB[l]); SNF_CHECK_ALIGN(gW[l], 16); }
   bf::Bf16Ws w = bf::bf16_layout(ws, M, 1);
-  return snf_bf16_backward(grad_out, M, packed, w, gW, gB, num_sms(), (cudaStream_t)stream);
+  int nsm = 0;
+  if (int e = snf_device_setup(&nsm)) return e;
+  return snf_bf16_backward(grad_out, M, packed, w, gW, gB, nsm, (cudaStream_t)stream);
 }

@@ -1,8 +1,9 @@
-// bf16 tensor-core backward of the field network (sm_100a).  Two persistent warp-specialised kernels over the
-// tile images the forward saved (snf_mlp_bf16.cu: enc, H_l = sin(pre_l), C_l = cos(pre_l), all [tile][..][128 x 512]
-// bf16 in the UMMA K-major SWIZZLE_128B image):
+// 16-bit tensor-core backward of the field network (sm_100a).  Two persistent warp-specialised kernels over the
+// tile images the forward saved (snf_mlp_bf16.cu: enc, H_l = sin(pre_l) as [tile][..][128 x 512] fp16 in the UMMA K-major
+// SWIZZLE_128B image, C_l = cos(pre_l) as one-byte codes).  All gradients images carry the power-of-two scale S of
+// GradScale (snf_bf16_common.cuh): fp16 operands need it for range, the wgrad flush divides it out exactly.
 //
-//  dgrad chain  (mlp_dgrad_bf16_kernel): per 128-point tile, dpre_7 = (g W_out) * C_7 in the epilogue warps, then for
+//  dgrad chain  (mlp_dgrad_bf16_kernel): per 128-point tile, dpre_7 = S (g W_out) * C_7 in the epilogue warps, then for
 //     l = 7..1:  dpre_{l-1} = (dpre_l W_l) * C_{l-1}  -- tcgen05.mma with A = dpre_l image in shared memory, B = W_l^T
 //     blocks streamed by TMA, D in TMEM; every dpre_l image is bulk-stored to HBM (D_l) for the weight gradients.
 //  wgrad        (mlp_wgrad_bf16_kernel): dW_l[o,i] = sum_p D_l[p,o] Hprev_l[p,i].  The saved images are read
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const flo
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = W[li][(o0 + j) * D + i];
   uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  o.x = pack_f16x2(v[0], v[1]); o.y = pack_f16x2(v[2], v[3]); o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
   dst[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
 }
 
@@ -47,16 +48,28 @@ struct DgradParams {
   int64_t M;
   int num_tiles;            // even
   const uint8_t *packed;    // forward pack + W^T blocks
-  const uint8_t *save_pre;  // [tiles][8][64 KB] cos(pre) as int8, C_BYTES layout (written by the forward)
-  uint8_t *save_d;          // [tiles][8][128 KB] dpre_l images (output)
+  const uint8_t *save_pre;  // [tiles][8][64 KB] cos(pre) codes, C_BYTES layout (written by the forward)
+  uint8_t *save_d;          // [tiles][8][128 KB] S dpre_l images, fp16 (output)
+  GradScale *scale;         // in: gmax_bits (absmax_kernel); out: S, 1/S (written by CTA 0 for the wgrad)
 };
 
+// max |g| over the whole batch as the bit pattern of a non-negative float (ordered like an unsigned; a NaN wins)
+__global__ void __launch_bounds__(256) absmax_kernel(const float2 *__restrict__ g, int64_t M, uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = __ldg(g + i);
+    m = max(m, max(__float_as_uint(fabsf(v.x)), __float_as_uint(fabsf(v.y))));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(kFull, m, d));
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m);
+}
 
 __device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-// dpre_{l-1} = (dpre_l W_l) * cos(pre_{l-1}); the cosines come from the forward as int8 (C_BYTES images).
+// dpre_{l-1} = (dpre_l W_l) * cos(pre_{l-1}); the cosines come from the forward as one-byte codes (C_BYTES images).
 // Same overlapped structure as the forward (snf_mlp_bf16.cu): per layer two temporal N-halves, the epilogue of half 0
 // runs under the MMAs of half 1 and keeps its result in registers until the A image may be overwritten; the next
 // layer's MMAs start slab by slab.  Shared-memory layout and barriers: namespace fw (the bias area is unused).
@@ -126,7 +139,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
     int s = 0; uint32_t ph = 0;
     if (rank == 0) {
       // =========================== MMA issuer (leader CTA); see the forward kernel
-      const uint32_t idesc = idesc_bf16(256, NCHUNK);
+      const uint32_t idesc = idesc_f16kind(256, NCHUNK, FMT, FMT);
       const uint64_t adesc0 = smem_desc(sA, 16, 1024), bdesc0 = smem_desc(sW, 16, 1024);
       uint32_t rph = 0;
       auto wait_ready = [&](int k) { mbar_wait(bar.ready(k), (rph >> k) & 1u); rph ^= 1u << k; };
@@ -205,21 +218,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         else mbar_arrive_remote_relaxed(ready_addr[k]);
       }
     };
-    // this thread's CPT cosines of one step: CPT / 16 x 16 int8, offset-binary after the XOR (cosq_get)
+    // the scale of this backward call: the same S in every CTA (same inputs, same arithmetic); CTA 0 publishes it
+    float gscale;
+    {
+      float wm = 0.f;
+      for (int j = lane; j < D; j += 32) wm = fmaxf(wm, fabsf(wout_s[j]) + fabsf(wout_s[D + j]));
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) wm = fmaxf(wm, __shfl_xor_sync(kFull, wm, d));
+      gscale = grad_scale_from(__uint_as_float(__ldg(&p.scale->gmax_bits)), wm);
+      if (blockIdx.x == 0 && e == 0 && lane == 0) { p.scale->S = gscale; p.scale->invS = 1.f / gscale; }
+    }
+    // this thread's CPT cosine codes of one step: CPT / 16 x 16 bytes (cosq_dec2)
     constexpr int NQ = CPT / 16;
     auto load_pre = [&](const uint8_t *img, int sl, uint4 (&pv)[NQ]) {
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
-        uint4 v = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 4 + g * NQ + k) * TILE_M + row) << 4)));
-        v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
-        pv[k] = v;
-      }
+      for (int k = 0; k < NQ; ++k)
+        pv[k] = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 4 + g * NQ + k) * TILE_M + row) << 4)));
     };
-    auto cos_of = [&](const uint4 (&pv)[NQ], int i) {   // element i (0 .. CPT-1) of the step
-      const uint4 &v = pv[i >> 4];
-      const int wi = (i >> 2) & 3;
-      const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
-      return cosq_get(w, i & 3);
+    // (a0, a1) * (cos code 2 pr, 2 pr + 1 of w) as an fp16 pair
+    auto mul2 = [&](float a0, float a1, __half2 c) {
+      const __half2 r = __hmul2(__floats2half2_rn(a0, a1), c);
+      return *reinterpret_cast<const uint32_t *>(&r);
     };
     // hand complete slabs to the MMA issuer first (ready barrier k, or none), then to the store warp (wrote[slot])
     auto publish = [&](int slot, int k) {
@@ -242,7 +261,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
         const uint8_t *p7 = pre_tile + (int64_t)(NH - 1) * C_BYTES;
         load_pre(p7, 0, pn);
         float2 gg = make_float2(0.f, 0.f);
-        if (m < p.M) gg = p.g[m];
+        if (m < p.M) { gg = p.g[m]; gg.x *= gscale; gg.y *= gscale; }
         if (!first_tile) wait_afree();                // the previous tile's last stores have left the A image
         first_tile = false;
 #pragma unroll
@@ -257,11 +276,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             const int col = sl * 64 + (CHUNKS * g + c) * 8;
             const float4 wa0 = *reinterpret_cast<const float4 *>(wout_s + col), wa1 = *reinterpret_cast<const float4 *>(wout_s + col + 4);
             const float4 wb0 = *reinterpret_cast<const float4 *>(wout_s + D + col), wb1 = *reinterpret_cast<const float4 *>(wout_s + D + col + 4);
+            const uint4 &cv = pv[c >> 1];             // 8 codes of this chunk: two words
+            const uint32_t cw0 = (c & 1) ? cv.z : cv.x, cw1 = (c & 1) ? cv.w : cv.y;
             uint4 o;
-            o.x = pack_bf16x2((gg.x * wa0.x + gg.y * wb0.x) * cos_of(pv, 8 * c + 0), (gg.x * wa0.y + gg.y * wb0.y) * cos_of(pv, 8 * c + 1));
-            o.y = pack_bf16x2((gg.x * wa0.z + gg.y * wb0.z) * cos_of(pv, 8 * c + 2), (gg.x * wa0.w + gg.y * wb0.w) * cos_of(pv, 8 * c + 3));
-            o.z = pack_bf16x2((gg.x * wa1.x + gg.y * wb1.x) * cos_of(pv, 8 * c + 4), (gg.x * wa1.y + gg.y * wb1.y) * cos_of(pv, 8 * c + 5));
-            o.w = pack_bf16x2((gg.x * wa1.z + gg.y * wb1.z) * cos_of(pv, 8 * c + 6), (gg.x * wa1.w + gg.y * wb1.w) * cos_of(pv, 8 * c + 7));
+            o.x = mul2(gg.x * wa0.x + gg.y * wb0.x, gg.x * wa0.y + gg.y * wb0.y, cosq_dec2<0>(cw0));
+            o.y = mul2(gg.x * wa0.z + gg.y * wb0.z, gg.x * wa0.w + gg.y * wb0.w, cosq_dec2<1>(cw0));
+            o.z = mul2(gg.x * wa1.x + gg.y * wb1.x, gg.x * wa1.y + gg.y * wb1.y, cosq_dec2<0>(cw1));
+            o.w = mul2(gg.x * wa1.z + gg.y * wb1.z, gg.x * wa1.w + gg.y * wb1.w, cosq_dec2<1>(cw1));
             *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) = o;
           }
           publish(sl, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
@@ -290,10 +311,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             else if (!last) load_pre(pnext, 0, pn);
             uint32_t pk[CPT / 2];
             auto part16 = [&](const uint32_t (&a)[16], int c0) {   // 16 columns = chunks c0, c0 + 1 of this step
+              const uint4 &cv = pv[c0 >> 1];
+              const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
-              for (int i = 0; i < 16; i += 2)
-                pk[4 * c0 + i / 2] = pack_bf16x2(__uint_as_float(a[i]) * cos_of(pv, 8 * c0 + i),
-                                                 __uint_as_float(a[i + 1]) * cos_of(pv, 8 * c0 + i + 1));
+              for (int i = 0; i < 16; i += 4) {
+                pk[4 * c0 + i / 2] = mul2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]), cosq_dec2<0>(cw[i >> 2]));
+                pk[4 * c0 + i / 2 + 1] = mul2(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]), cosq_dec2<1>(cw[i >> 2]));
+              }
             };
             if (CPT == 32) {
               tmem_ld_wait(accA);
@@ -358,6 +382,7 @@ static_assert(WG_SMEM_BYTES <= 232448, "wgrad ring exceeds shared memory");
 
 struct WgradParams {
   const uint8_t *save_d, *save_h, *save_enc;
+  const GradScale *scale;   // 1/S written by the dgrad chain
   int num_tiles, tiles_per_item, num_items;
   float *gW[NH];
   float *gB[NH];
@@ -435,7 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
     int s = 0; uint32_t ph = 0;
     if (rank == 0) {
       // MMA issuer: the whole warp runs the uniform control flow, one elected lane issues
-      const uint32_t idesc256 = idesc_bf16(256, 256, 1, 1), idesc128 = idesc_bf16(256, 128, 1, 1);
+      const uint32_t idesc256 = idesc_f16kind(256, 256, FMT, FMT, 1, 1), idesc128 = idesc_f16kind(256, 128, FMT, FMT, 1, 1);
       const uint64_t desc0 = smem_desc(base, WG_SLAB_STAGE, 1024);   // MN-major: LBO = slab stride in the stage, SBO = 8-point groups
       uint32_t ph_free = 0;
       bool first_item = true;
@@ -487,6 +512,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t accfree_addr = rank == 0 ? bar_accfree : mapa_shared(bar_accfree, 0);
     int s = 0; uint32_t ph = 0, ph_acc = 0;
+    const float inv_s = __ldg(&p.scale->invS);          // the D images hold S dL/dpre
     for (int item = pair; item < p.num_items; item += npairs) {
       int l, ob, t0, t1; decode(item, l, ob, t0, t1);
       const int o = ob * 256 + (int)rank * 128 + row;
@@ -500,13 +526,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
 #pragma unroll 8
           for (int r = 0; r < WG_KSTAGE; ++r) {
             const uint16_t v = *reinterpret_cast<const uint16_t *>(st + sw128_chunk_off(r, bc8) + be * 2);
-            bsum += __uint_as_float((uint32_t)v << 16);
+            bsum += __half2float(__ushort_as_half(v));
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty(s));
           if (++s == WG_NSTAGE) { s = 0; ph ^= 1; }
         }
-      atomicAdd(p.gB[l] + o, bsum);
+      atomicAdd(p.gB[l] + o, bsum * inv_s);
       // ---- flush dW_l[o, :]
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tcgen05_fence_after();
@@ -525,8 +551,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) mlp_w
             if (col >= 88) continue;          // zero padding of the encoder image
             if (col >= 84) col -= 84;         // residual columns fold back onto the raw-coordinate weights
           }
-          red_add_v4(wrow + col, __uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
-                     __uint_as_float(acc[i + 3]));
+          red_add_v4(wrow + col, __uint_as_float(acc[i]) * inv_s, __uint_as_float(acc[i + 1]) * inv_s,
+                     __uint_as_float(acc[i + 2]) * inv_s, __uint_as_float(acc[i + 3]) * inv_s);
         }
       }
       tcgen05_fence_before();
@@ -573,8 +599,8 @@ __global__ void __launch_bounds__(OW_THREADS) out_wgrad_bf16_kernel(const float2
       }
 #pragma unroll
       for (int i = 0; i < OW_ROWS; ++i) {
-        const float h[8] = {bf_lo(hv[i].x), bf_hi(hv[i].x), bf_lo(hv[i].y), bf_hi(hv[i].y),
-                            bf_lo(hv[i].z), bf_hi(hv[i].z), bf_lo(hv[i].w), bf_hi(hv[i].w)};
+        const float h[8] = {h_lo(hv[i].x), h_hi(hv[i].x), h_lo(hv[i].y), h_hi(hv[i].y),
+                            h_lo(hv[i].z), h_hi(hv[i].z), h_lo(hv[i].w), h_hi(hv[i].w)};
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a0[j] = fmaf(gg[i].x, h[j], a0[j]); a1[j] = fmaf(gg[i].y, h[j], a1[j]); }
         if (cg == 0) { s0 += gg[i].x; s1 += gg[i].y; }
@@ -645,16 +671,15 @@ static int debug_sync(const char *what, cudaStream_t st) {
   return 0;
 }
 
+int snf_bf16_set_attributes_bwd() {
+  cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(bf::mlp_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::WG_SMEM_BYTES);
+  return (int)e;
+}
+
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
                       float *const *gB, int num_sms, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(bf::mlp_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::WG_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
   int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
   num_tiles = (num_tiles + 1) / 2 * 2;   // CTA pairs; the workspace is sized for the padding tile
   // gradients are accumulated with atomics: clear them first (ABI: overwritten).  The trainer hands views of one flat
@@ -672,11 +697,18 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
     for (int l = 0; l <= bf::NH; ++l) { add(gW[l], wsz[l]); add(gB[l], l < bf::NH ? 512 : 2); }
     flush();
   }
+  // max |g| of the batch -> the power-of-two scale of the fp16 gradient images (GradScale)
+  cudaMemsetAsync(w.scale, 0, sizeof(bf::GradScale), st);
+  {
+    int64_t ablocks = ceil_div64(M, 256);
+    if (ablocks > 2 * num_sms) ablocks = 2 * num_sms;
+    bf::absmax_kernel<<<(unsigned)ablocks, 256, 0, st>>>(reinterpret_cast<const float2 *>(grad_out), M, &w.scale->gmax_bits);
+  }
   bf::DgradParams dp{};
   dp.g = reinterpret_cast<const float2 *>(grad_out);
   dp.M = M; dp.num_tiles = num_tiles;
   dp.packed = reinterpret_cast<const uint8_t *>(packed);
-  dp.save_pre = w.pre; dp.save_d = w.d;
+  dp.save_pre = w.pre; dp.save_d = w.d; dp.scale = w.scale;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   grid &= ~1;
   BWD_EV(0);
@@ -685,7 +717,7 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   if (int e = debug_sync("mlp_dgrad_bf16_kernel", st)) return e;
 
   bf::WgradParams wp{};
-  wp.save_d = w.d; wp.save_h = w.h; wp.save_enc = w.enc;
+  wp.save_d = w.d; wp.save_h = w.h; wp.save_enc = w.enc; wp.scale = w.scale;
   wp.num_tiles = num_tiles;
   // items = tile ranges x 8 layers x 2 o-blocks, about 7 per CTA pair
   const int npairs = num_sms / 2;
@@ -703,6 +735,6 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   bf::out_wgrad_bf16_kernel<<<ogrid, bf::OW_THREADS, 0, st>>>(dp.g, M, num_tiles, w.h, gW[bf::NH], gB[bf::NH]);
   BWD_EV(3);
   if (g_time_bwd) ++g_bwd_calls;
-  count_launch(3);
+  count_launch(4);
   return launch_status();
 }

@@ -7,6 +7,7 @@
 namespace snf {
 
 unsigned long long g_launches = 0;
+DeviceState g_devices[kMaxDevices];
 
 // ------------------------------------------------------------------------------------------------
 // K1: one warp per 32 rays.  Lane r computes the shell entry/exit of ray r once (two square roots and a
@@ -285,6 +286,17 @@ extern "C" const char *snf_error_string(int code) {
   }
 }
 
+// hier_kernel needs up to 51 KB of dynamic shared memory at its accepted limits (S = 256, n_new = 512): opt in per device
+constexpr int kHierMaxSmem = 64 * 1024;
+int snf_sampling_set_attributes() {
+  cudaError_t e = cudaSuccess;
+#define SNF_ATTR(PER) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hier_kernel<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHierMaxSmem)
+  SNF_ATTR(1); SNF_ATTR(2); SNF_ATTR(4); SNF_ATTR(8); SNF_ATTR(16);
+#undef SNF_ATTR
+  return (int)e;
+}
+
 extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals,
                                      const float *t_rand, int64_t N, int S, float distance, float solar_R,
                                      float *z_vals, float *points, void *stream) {
@@ -313,6 +325,9 @@ extern "C" int snf_hier_resample(const float *z_vals, const float *weights, cons
   const int warps = 4;
   const int ncnt = (S > n_new ? S : n_new) + 2;
   const size_t smem = ((size_t)n_new + (size_t)warps * (3 * S + n_new + (S + n_new) + 2 * S + ncnt)) * sizeof(float);
+  if (smem > (size_t)kHierMaxSmem) return SNF_E_SHAPE;
+  if (smem > 48 * 1024)
+    if (int e = snf_device_setup(nullptr)) return e;
   const unsigned grid = (unsigned)ceil_div64(N, warps);
 #define SNF_LAUNCH(PER) \
   hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out)

@@ -4,6 +4,7 @@
 // included, so the kernels build with nvcc alone.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -182,6 +183,16 @@ __host__ __device__ __forceinline__ uint32_t idesc_bf16(int M, int N, int a_mn_m
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with independently chosen 16-bit operand formats (0 = F16, 1 = BF16) and FP32 accumulate.  The field
+// network runs A = fp16 activations x B = fp16 weights in the forward, A = bf16 dL/dpre x B = fp16 (W^T, h) in the
+// backward: fp16's 11-bit significand is what the 1e-3 gradient gate needs of the weights, bf16's exponent range what
+// the back-propagated gradients need (tools/micro/bf16_grad_study.py; mixed formats checked by tools/umma_probe.cu).
+enum : int { FMT_F16 = 0, FMT_BF16 = 1 };
+__host__ __device__ __forceinline__ uint32_t idesc_f16kind(int M, int N, int a_fmt, int b_fmt, int a_mn_major = 0,
+                                                           int b_mn_major = 0) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]   (issued by ONE thread)
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -287,6 +298,10 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int r, int c8) {
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
 }
 

@@ -6,7 +6,8 @@ out_layer.{weight,bias}, log_absortpion.{94,...,335}, volumetric_constant.  Modu
 reference's order, so `torch.manual_seed(s)` gives bit-identical initial weights.
 
 Extra (non-reference) knob: `precision` = 'fp32' (FFMA SIMT, the 1e-5 parity mode) or 'bf16' (tcgen05 tensor
-cores, the 1e-2 mode); default from $SUNERF_B200_PRECISION, else 'fp32'.
+cores, the task's "bf16-MLP mode": 1e-2 on intensities, 1e-3 on gradients; its MMA operands are fp16 since round 2,
+'f16' / 'fp16' are accepted as aliases); default from $SUNERF_B200_PRECISION, else 'fp32'.
 """
 from __future__ import annotations
 
@@ -20,26 +21,33 @@ from . import ops
 from ._lib import SnfError
 
 
-def default_precision() -> str:
-    p = os.environ.get('SUNERF_B200_PRECISION', 'fp32').lower()
+def canonical_precision(p: str) -> str:
+    p = str(p).lower()
+    if p in ('f16', 'fp16', 'tc'):
+        p = 'bf16'
     if p not in ('fp32', 'bf16'):
-        raise ValueError(f'SUNERF_B200_PRECISION must be fp32 or bf16, got {p}')
+        raise ValueError(f'precision must be fp32 or bf16, got {p}')
     return p
 
 
+def default_precision() -> str:
+    return canonical_precision(os.environ.get('SUNERF_B200_PRECISION', 'fp32'))
+
+
 class Sine(nn.Module):
-    """model.py:66-72 (kept for state/structure compatibility; the kernels fuse it)."""
+    """model.py:66-72.  The field-network kernels fuse it; called on its own it is the reference's one torch op."""
 
     def __init__(self, w0: float = 1.):
         super().__init__()
         self.w0 = w0
 
     def forward(self, x):
-        raise SnfError('Sine is fused into the field-network kernels; call the owning model instead')
+        return torch.sin(self.w0 * x)
 
 
 class PositionalEncoding(nn.Module):
-    """model.py:92-132: holds `freq_bands` (buffer, state_dict key) - the encoding itself is fused."""
+    """model.py:92-132: holds `freq_bands` (buffer, state_dict key).  The field-network kernels fuse the encoding; called
+    on its own (model.py:123-132) it is the reference's torch expression: [x, sin(x f / s) (f major), cos(same)]."""
 
     def __init__(self, d_input: int, n_freqs: int, scale_factor: float = 2., log_space: bool = True):
         super().__init__()
@@ -51,7 +59,8 @@ class PositionalEncoding(nn.Module):
         self.scale_factor = scale_factor
 
     def forward(self, x):
-        raise SnfError('PositionalEncoding is fused into the field-network kernels; call the owning model instead')
+        arg = x[:, None, :] * self.freq_bands[None, :, None] / self.scale_factor
+        return torch.cat([x, torch.sin(arg).reshape(x.shape[0], -1), torch.cos(arg).reshape(x.shape[0], -1)], dim=-1)
 
 
 class _FieldMLP(torch.autograd.Function):
@@ -96,7 +105,7 @@ class NeRF(nn.Module):
         self.in_layer = nn.Sequential(enc, nn.Linear(enc.d_output, d_filter))
         self.layers = nn.ModuleList([nn.Linear(d_filter, d_filter) for _ in range(n_layers - 1)])
         self.out_layer = nn.Linear(d_filter, d_output)
-        self.precision = default_precision() if precision is None else precision
+        self.precision = default_precision() if precision is None else canonical_precision(precision)
         self._pack = None          # (raw tensor, aligned ptr)
         self._pack_key = None
 
@@ -112,8 +121,7 @@ class NeRF(nn.Module):
         return 0.0, 0.0
 
     def _packed_ptr(self, weights, biases):
-        # the TS inference variant reads its own stage order, packed only while it is selected
-        key = (ops.fwd_variant(),) + tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+        key = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
         if self._pack is None or self._pack[0].device != weights[0].device:
             self._pack = ops.alloc_packed(weights[0].device)
             self._pack_key = None

@@ -117,12 +117,6 @@ class MLPWorkspace:
         self.ptr = (self._raw.data_ptr() + 1023) // 1024 * 1024
 
 
-def fwd_variant(variant: Optional[int] = None) -> int:
-    """Kernel behind the bf16 inference forward: 0 = activation operand in shared memory (SS), 1 = in tensor memory (TS).
-    Sets it when given, returns the previous value."""
-    return int(_lib.lib().snf_debug_fwd_variant(-1 if variant is None else int(variant)))
-
-
 def pack_bytes() -> int:
     return int(_lib.lib().snf_mlp_pack_bytes())
 

@@ -88,15 +88,21 @@ class RayStore:
     def epoch_order(self, shuffle: bool = True) -> List[int]:
         return dataloader_batch_order(len(self)) if shuffle else list(range(len(self)))
 
-    def batch(self, idx: int) -> Dict[str, torch.Tensor]:
-        """This rank's contiguous share of global batch `idx` (rows [idx B, (idx+1) B) of the files, dataset.py:23-27;
-        the last batch may be short, and is split like torch's scatter: ceil-sized leading chunks)."""
+    def shard_range(self, idx: int, rank: Optional[int] = None):
+        """Row range [a, b) of global batch `idx` that `rank` owns.  The batch is rows [idx B, (idx+1) B) of the files
+        (dataset.py:23-27; the last one may be short) and is split as evenly as `parallel.shard_rows` does: shards differ
+        by at most one ray and none is empty while the batch has at least `world` rays.  (torch's 'dp' scatter hands out
+        ceil-sized chunks and simply uses fewer replicas on a short tail; one process per GPU cannot drop a rank out of
+        the all-reduce, and an empty shard is a no-op step there - see RayTrainer.step.)"""
         if not 0 <= idx < len(self):
             raise IndexError(idx)
         lo, hi = idx * self.batch_size, min((idx + 1) * self.batch_size, self.n_rays)
-        n = hi - lo
-        per = -(-n // self.world)
-        a, b = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
+        sl = parallel.shard_rows(hi - lo, self.rank if rank is None else rank, self.world)
+        return lo + sl.start, lo + sl.stop
+
+    def batch(self, idx: int) -> Dict[str, torch.Tensor]:
+        """This rank's contiguous share of global batch `idx` as zero-copy views."""
+        a, b = self.shard_range(idx)
         return {k: v[a:b] for k, v in self.data.items()}
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:

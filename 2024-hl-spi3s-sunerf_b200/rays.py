@@ -3,7 +3,7 @@
 regular helioprojective pixel grid, as SURVEY.md section 8d specifies for the synthetic workloads."""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -12,16 +12,19 @@ SOLRAD_M = 6.957e8
 R_OBS = 1.495978707e11 / SOLRAD_M      # 1 AU in solar radii
 
 
-def pose_spherical(theta: float, phi: float, radius: float) -> np.ndarray:
-    """camera-to-world: translate along z, rotate by phi about x, by theta about y, then the axis flip."""
-    c2w = np.eye(4, dtype=np.float32)
-    c2w[2, 3] = radius
-    cp, sp_ = np.cos(phi), np.sin(phi)
-    ct, st = np.cos(theta), np.sin(theta)
-    rot_phi = np.array([[1, 0, 0, 0], [0, cp, -sp_, 0], [0, sp_, cp, 0], [0, 0, 0, 1]], dtype=np.float32)
-    rot_theta = np.array([[ct, 0, -st, 0], [0, 1, 0, 0], [st, 0, ct, 0], [0, 0, 0, 1]], dtype=np.float32)
+def pose_spherical(theta: float, phi: float, radius: float, shift: Optional[Sequence[float]] = None) -> np.ndarray:
+    """sunerf/train/coordinate_transformation.py:36-54 - 4x4 camera-to-world pose, float32 matrix products in the
+    reference's order: flip @ rot_theta @ rot_phi @ trans_t, then the optional translation.  (The one host-side
+    definition of the package.)"""
+    t = np.eye(4, dtype=np.float32); t[2, 3] = radius
+    rp = np.array([[1, 0, 0, 0], [0, np.cos(phi), -np.sin(phi), 0], [0, np.sin(phi), np.cos(phi), 0], [0, 0, 0, 1]], dtype=np.float32)
+    rt = np.array([[np.cos(theta), 0, -np.sin(theta), 0], [0, 1, 0, 0], [np.sin(theta), 0, np.cos(theta), 0], [0, 0, 0, 1]], dtype=np.float32)
     flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
-    return flip @ (rot_theta @ (rot_phi @ c2w))
+    c2w = flip @ (rt @ (rp @ t))
+    if shift is not None:
+        ts = np.eye(4, dtype=np.float32); ts[:3, 3] = np.asarray(shift, dtype=np.float32)
+        c2w = ts @ c2w
+    return c2w
 
 
 def observer_rays(H: int, W: int, plate_arcsec: float, lat_deg: float, lon_deg: float,

@@ -10,7 +10,8 @@ pass.  `rendering.state_dict()` keeps the reference's keys and shapes.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from collections import OrderedDict
+from typing import Any, Dict, Optional
 
 import torch
 
@@ -52,7 +53,13 @@ class RayTrainer:
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         self.step_count = 0
+        self.lr0 = lr
         self._flatten()
+        if self.world > 1:
+            # replicas must start identical: rank 0's parameters win (a differently seeded or differently restored rank
+            # would otherwise diverge silently while the all-reduce keeps succeeding)
+            torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
         self.scratch = torch.zeros(1024, device=self.dev)
         self.grad_norm = torch.zeros(1, device=self.dev)
         self.finite_flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
@@ -94,12 +101,25 @@ class RayTrainer:
         self.exp_avg = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.grad_view = {}
+        self.segment = {}          # id(parameter) -> (offset, numel) in the flat buffers
+        self._segs = segs
         with torch.no_grad():
             for p, o in segs:
                 n = p.numel()
                 self.flat[o:o + n].copy_(p.detach().reshape(-1).to(self.dev))
                 p.data = self.flat[o:o + n].view(p.shape)
                 self.grad_view[id(p)] = self.flat_grad[o:o + n].view(p.shape)
+                self.segment[id(p)] = (o, n)
+
+    def _check_homed(self):
+        """The parameters are views into `self.flat`; `rendering.to(device)`, `.half()`, `.float()` or a checkpoint load that
+        REPLACES `p.data` would silently detach them (the kernels would keep training the flat buffer, the module would
+        keep its stale copy).  Checked once per step on the first and last segment - a module-wide move changes both."""
+        for p, o in (self._segs[0], self._segs[-1]):
+            if p.data_ptr() != self.flat.data_ptr() + 4 * o or p.device != self.dev or p.dtype != torch.float32:
+                raise SnfError('the rendering module was moved / re-typed / re-allocated after RayTrainer took ownership of its '
+                               'parameters (they are views into one flat buffer): build a new RayTrainer, or load weights '
+                               'with load_state_dict / copy_ (in place)')
 
     def _grads(self, model):
         ps = model.linear_params()
@@ -120,6 +140,12 @@ class RayTrainer:
         # host (pinned) tensors are accepted: eager steps move them to the device, replays copy them straight into the
         # graph's static input buffers
         to_dev = lambda x: x if (x is None or x.is_cuda) else x.to(self.dev, non_blocking=True)
+        self._check_homed()
+        if torch.cuda.current_device() != self.dev.index:
+            with torch.cuda.device(self.dev):          # the C ABI launches on the CURRENT device's stream
+                return self.step(rays_o, rays_d, times, target, wavelengths, t_rand)
+        if rays_o.shape[0] == 0:
+            return self._empty_step()
         if not self.use_cuda_graph:
             return self._step_impl(to_dev(rays_o), to_dev(rays_d), to_dev(times), to_dev(target), to_dev(wavelengths),
                                    to_dev(t_rand), device_sched=self._device_sched)
@@ -155,6 +181,29 @@ class RayTrainer:
         _lib.lib().snf_count_launches(self._g_launches)
         self._host_bookkeeping()
         return self._g_out
+
+    def _empty_step(self) -> Dict[str, torch.Tensor]:
+        """A rank whose shard of a (tail) batch is empty still joins both all-reduces - with zero gradients - and applies the
+        same optimiser step as everybody else, so the replicas stay identical and nobody hangs in NCCL."""
+        self.flat_grad.zero_()
+        # same issue order as _step_impl: coarse bucket first
+        parallel.wait_all([self._reduce_async('coarse_model'), self._reduce_async('fine_model')])
+        self._optimizer_step(self._device_sched)
+        self._host_bookkeeping()
+        nan = torch.full((4,), float('nan'), device=self.dev)
+        C = 0
+        return {'losses': nan, 'psnr': nan[0], 'coarse_image': torch.empty(0, C, device=self.dev),
+                'fine_image': torch.empty(0, C, device=self.dev), 'grad_norm': self.grad_norm,
+                'z_vals_hierarchical': torch.empty(0, self.r.sampler_hierarchical.n_samples, device=self.dev)}
+
+    def _optimizer_step(self, device_sched: bool):
+        # grads averaged over ranks == Lightning dp's mean of replica losses
+        if device_sched:
+            ops.adam_step_sched(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.sched, self.scratch,
+                                self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
+        else:
+            ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count + 1, self.lr, self.scratch,
+                          self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
 
     def _host_bookkeeping(self):
         self.step_count += 1
@@ -203,6 +252,9 @@ class RayTrainer:
             else:
                 g_raw_c = ops.composite_emission_bwd(raw_c, z, rays_d, g_ic.view(-1), None)
             ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
+            # the coarse bucket is exchanged as soon as it exists (a millisecond before the fine backward ends): NCCL's
+            # CTAs slot into the tails of the fine pass's persistent kernels instead of queueing up behind the step
+            h_coarse = self._reduce_async('coarse_model')
         # ---- fine pass
         new_z, z_comb = r.sampler_hierarchical.resample(z, wts_c)
         Sf = z_comb.shape[1]
@@ -230,15 +282,9 @@ class RayTrainer:
         h_fine = self._reduce_async('fine_model')
         if side is not main:
             main.wait_stream(side)
-        h_coarse = self._reduce_async('coarse_model')
-        parallel.wait_all([h_fine, h_coarse])
-        # ---- optimiser (grads averaged over ranks == Lightning dp's mean of replica losses)
-        if device_sched:
-            ops.adam_step_sched(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.sched, self.scratch,
-                                self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
-        else:
-            ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count + 1, self.lr, self.scratch,
-                          self.grad_norm, clip_norm=self.clip, grad_scale=1.0 / self.world)
+        parallel.wait_all([h_coarse, h_fine])
+        # ---- optimiser
+        self._optimizer_step(device_sched)
         if host_bookkeeping:
             self._host_bookkeeping()
         else:                                          # under capture: the next replay must re-pack the weights
@@ -257,3 +303,100 @@ class RayTrainer:
         """The reference asserts on NaN/Inf every step (sunerf.py:105-107); here it is one device flag read on demand."""
         if int(self.finite_flag.item()) != 0:
             raise AssertionError('! [Numerical Alert] a rendered output contains NaN or Inf')
+
+    # ------------------------------------------------------------------ optimiser / schedule state (resume)
+    # The reference resumes with `trainer.fit(ckpt_path='last')` (run_emission.py:38,75): Lightning restores the Adam
+    # moments and step counts (`optimizer_states`) and the ExponentialLR state (`lr_schedulers`) next to the weights.
+    def _sync_sched_from_device(self):
+        if self._device_sched:
+            lr, step = self.sched[:2].tolist()
+            self.lr, self.step_count = float(lr), int(round(step)) - 1
+
+    def state_dict(self) -> Dict[str, Any]:
+        """Flat optimiser state of this trainer (moments, step, lr); weights travel in `rendering.state_dict()`."""
+        self._sync_sched_from_device()
+        return {'exp_avg': self.exp_avg.detach().cpu().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().cpu().clone(),
+                'step_count': self.step_count, 'lr': self.lr, 'lr0': self.lr0, 'gamma': self.gamma, 'n_flat': self.n_flat}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        if int(sd['n_flat']) != self.n_flat:
+            raise SnfError(f"optimiser state is for {sd['n_flat']} flat parameters, this trainer has {self.n_flat}")
+        self.exp_avg.copy_(sd['exp_avg']); self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        self._set_schedule(float(sd['lr']), int(sd['step_count']))
+
+    def _set_schedule(self, lr: float, step_count: int):
+        self.lr, self.step_count = lr, step_count
+        self.sched.copy_(torch.tensor([lr, step_count + 1.0, self.gamma, 5e-5], dtype=torch.float64))
+        self._graph, self._g_key = None, None          # a captured step holds no host scalars, but start clean
+
+    def _adam_params(self):
+        return [p for p in self.r.parameters() if p.requires_grad]
+
+    def optimizer_state_dict(self) -> Dict[str, Any]:
+        """`torch.optim.Adam(rendering.parameters(), lr).state_dict()` layout (sunerf/model/sunerf.py:31), i.e. what
+        Lightning stores under checkpoint['optimizer_states'][0]: per-parameter step / exp_avg / exp_avg_sq in
+        `rendering.parameters()` order."""
+        self._sync_sched_from_device()
+        state = {}
+        params = self._adam_params()
+        if self.step_count > 0:
+            for i, p in enumerate(params):
+                o, n = self.segment[id(p)]
+                state[i] = {'step': torch.tensor(float(self.step_count)),
+                            'exp_avg': self.exp_avg[o:o + n].view(p.shape).detach().cpu().clone(),
+                            'exp_avg_sq': self.exp_avg_sq[o:o + n].view(p.shape).detach().cpu().clone()}
+        group = {'lr': self.lr, 'betas': (0.9, 0.999), 'eps': 1e-8, 'weight_decay': 0, 'amsgrad': False, 'maximize': False,
+                 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None, 'decoupled_weight_decay': False,
+                 'initial_lr': self.lr0, 'params': list(range(len(params)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_optimizer_state_dict(self, sd: Dict[str, Any]) -> None:
+        params = self._adam_params()
+        group = sd['param_groups'][0]
+        if len(group['params']) != len(params):
+            raise SnfError(f"optimizer state has {len(group['params'])} parameters, the rendering module has {len(params)}")
+        if tuple(group.get('betas', (0.9, 0.999))) != (0.9, 0.999) or abs(group.get('eps', 1e-8) - 1e-8) > 0:
+            raise SnfError('the fused optimiser implements the reference Adam (betas 0.9/0.999, eps 1e-8)')
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        steps = set()
+        for i, p in enumerate(params):
+            st = sd['state'].get(i, sd['state'].get(str(i)))
+            if st is None:
+                continue
+            o, n = self.segment[id(p)]
+            self.exp_avg[o:o + n].copy_(st['exp_avg'].reshape(-1)); self.exp_avg_sq[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(round(float(st['step']))))
+        if len(steps) > 1:
+            raise SnfError(f'parameters carry different Adam step counts {sorted(steps)}: one flat step count is kept')
+        self.lr0 = float(group.get('initial_lr', self.lr0))
+        self._set_schedule(float(group['lr']), steps.pop() if steps else 0)
+
+    def lr_scheduler_state_dict(self) -> Dict[str, Any]:
+        """`ExponentialLR.state_dict()` of sunerf.py:32-33: the schedule is stepped once per batch while lr > 5e-5."""
+        self._sync_sched_from_device()
+        import math
+        k = int(round(math.log(self.lr / self.lr0) / math.log(self.gamma))) if self.lr != self.lr0 else 0
+        return {'gamma': self.gamma, 'base_lrs': [self.lr0], 'last_epoch': k, '_step_count': k + 1,
+                '_get_lr_called_within_step': False, '_last_lr': [self.lr]}
+
+    def save_checkpoint(self, path: str, extra: Optional[Dict[str, Any]] = None) -> None:
+        """A Lightning-layout checkpoint (`state_dict` with the `rendering.` prefix of the reference's modules,
+        `optimizer_states`, `lr_schedulers`, `global_step`): the reference's `ckpt_path='last'` resume reads it, and
+        `load_checkpoint` restores a RayTrainer from the reference's own `last.ckpt`."""
+        sd = OrderedDict(('rendering.' + k, v.detach().cpu().clone()) for k, v in self.r.state_dict().items())
+        ck = {'state_dict': sd, 'optimizer_states': [self.optimizer_state_dict()],
+              'lr_schedulers': [self.lr_scheduler_state_dict()], 'global_step': self.step_count, 'epoch': 0,
+              'pytorch-lightning_version': '1.9.3'}
+        ck.update(extra or {})
+        torch.save(ck, path)
+
+    def load_checkpoint(self, path: str) -> Dict[str, Any]:
+        ck = torch.load(path, map_location='cpu', weights_only=True)
+        sd = {k[len('rendering.'):]: v for k, v in ck['state_dict'].items() if k.startswith('rendering.')}
+        self.r.load_state_dict(sd, strict=False)                    # sunerf.py:56-59 loads strict=False (in place: copy_)
+        self._check_homed()
+        if ck.get('optimizer_states'):
+            self.load_optimizer_state_dict(ck['optimizer_states'][0])
+        for name in ('fine_model', 'coarse_model'):
+            getattr(self.r, name)._pack_key = None
+        return ck

@@ -95,7 +95,8 @@ def synthetic_batch(n, seed):
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU PyTorch path for the same step (oracle port: same ATen ops as the reference, which
-    cannot travel to the GPU box), all host threads, on a bounded sample of the workload."""
+    cannot travel to the GPU box), all host threads.  Each step is the FULL 1024-ray step of the config (BASELINE.md
+    section 3) unless --ref-rays says otherwise; the line states the ray count it ran."""
     if rank != 0:
         return
     from oracle import sunerf_oracle as orc
@@ -123,8 +124,9 @@ def run_reference(args, rank, world):
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
             'config': workload_config(args.gpus),
-            'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{n} rays/step (of {RAYS_PER_GPU}) x {args.steps} steps, torch CPU fp32'},
+            'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'rays_per_step': n,
+                             'sample': (f'the full {n}-ray train step' if n == RAYS_PER_GPU else f'{n} of the {RAYS_PER_GPU} rays per step')
+                                       + f' x {args.steps} steps after {args.warmup} warm-up, torch CPU fp32 oracle, {cores} threads'},
             'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -138,7 +140,9 @@ def workload_config(gpus):
             'l2': 'per-step working set (saved layer activations, >1 GB) exceeds the 126 MB L2; no explicit flush'}
 
 
-def cpu_baseline(sample_rays=256):
+def cpu_baseline(sample_rays=RAYS_PER_GPU, render_rays=RENDER_BATCH):
+    """1 warm-up + best of 3 of the full train step at the config's ray count, and of a forward-only
+    render batch of 4096 rays, on all host cores (about 25 s of CPU work on the 16-core box)."""
     from oracle import sunerf_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -148,7 +152,7 @@ def cpu_baseline(sample_rays=256):
     cfg = orc.RenderConfig(kind='emission')
     gen = torch.Generator().manual_seed(3)
     best = None
-    for i in range(3):   # 1 warm-up + best of 2
+    for i in range(4):   # 1 warm-up + best of 3
         t_rand = torch.rand(sample_rays, 64, generator=gen)
         t0 = time.perf_counter()
         orc.train_step(cfg, pc, pf, opt, b['rays_o'], b['rays_d'], b['times'], b['target'], None, t_rand)
@@ -157,17 +161,18 @@ def cpu_baseline(sample_rays=256):
             best = dt if best is None else min(best, dt)
     # forward-only rendering of the same rays (the `render` metric's CPU counterpart)
     rbest = None
+    rb = synthetic_batch(render_rays, seed=1)
     with torch.no_grad():
-        for i in range(3):
+        for i in range(4):
             t0 = time.perf_counter()
-            orc.render(cfg, pc, pf, b['rays_o'], b['rays_d'], b['times'], None, None)
+            orc.render(cfg, pc, pf, rb['rays_o'], rb['rays_d'], rb['times'], None, None)
             dt = time.perf_counter() - t0
             if i > 0:
                 rbest = dt if rbest is None else min(rbest, dt)
-    return {'value': sample_rays / best, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-            'sample': f'1 warm-up + best of 2 full train steps on {sample_rays} of the {RAYS_PER_GPU} rays, torch CPU fp32 oracle',
-            'render_Msamples_per_s': sample_rays * (S_COARSE + S_FINE) / rbest / 1e6,
-            'render_sample': f'1 warm-up + best of 2 forward-only renders of {sample_rays} rays'}
+    return {'value': sample_rays / best, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'rays_per_step': sample_rays,
+            'sample': f'1 warm-up + best of 3 full train steps of {sample_rays} rays (the config size), torch CPU fp32 oracle, {cores} threads',
+            'render_Msamples_per_s': render_rays * (S_COARSE + S_FINE) / rbest / 1e6,
+            'render_sample': f'1 warm-up + best of 3 forward-only renders of one {render_rays}-ray batch'}
 
 
 # ------------------------------------------------------------------------------------------ this repo's arm
@@ -178,7 +183,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
-    ap.add_argument('--ref-rays', type=int, default=128)
+    ap.add_argument('--ref-rays', type=int, default=RAYS_PER_GPU, help='rays per step of the reference arm (default: the full config batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial-backward', action='store_true', help='coarse backward after the fine one instead of beside it (A/B aid)')
     ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~30 kernels of a step one by one instead of replaying a graph')
@@ -320,6 +325,32 @@ def main():
     renderer.render_observer_image(0.05, 1.0, 3.0, batch_size=RENDER_BATCH, rows=slice(0, 16), as_numpy=False)   # warm-up
     ms_image = timed_loop(image_once, 1)
 
+    # ---- render_mhd.yaml as shipped (BASELINE.json configs[4]): density-temperature head, C = 6, pixel_intensity_factor
+    #      1e10 (image_render.py:267), field = SimpleStar (render_mhd.yaml:1) and a trained-size NeRF_DT: a 4096-ray batch
+    #      and the 1024^2 image each
+    wl6 = torch.tensor([94., 171., 193., 211., 304., 335.], device=dev)
+    mhd = {}
+    for field in ('SimpleStar', 'NeRF_DT'):
+        torch.manual_seed(7)
+        kw = {'model': s.SimpleStar} if field == 'SimpleStar' else {'model': s.NeRF_DT, 'model_config': {'precision': args.precision}}
+        rmhd = s.DensityTemperatureRadiativeTransfer(Rs_per_ds=1, pixel_intensity_factor=1e10, **kw).to(dev)
+        wlb = wl6[None].expand(RENDER_BATCH, 6).contiguous()
+
+        def render_mhd_once():
+            with torch.no_grad():
+                return rmhd(rdev['rays_o'], rdev['rays_d'], rdev['times'], wlb)
+        for _ in range(3):
+            render_mhd_once()
+        nrep = max(3, args.steps // 2)
+        ms_b = timed_loop(render_mhd_once, nrep) / nrep
+        ren = s.ObserverRenderer(rmhd, (1024, 1024), plate_arcsec=2.4)
+        ren.render_observer_image(0.05, 1.0, 3.0, wl=wl6.cpu().numpy(), batch_size=RENDER_BATCH, rows=slice(0, 16), as_numpy=False)
+        ms_i = timed_loop(lambda: ren.render_observer_image(0.05, 1.0, 3.0, wl=wl6.cpu().numpy(), batch_size=RENDER_BATCH, rows=rows,
+                                                            as_numpy=False), 1)
+        mhd[field] = {'batch_4096': {'ms': ms_b, 'Msamples_per_s': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_b * 1e-3) / 1e6},
+                      'image_1024': {'ms': ms_i, 'Msamples_per_s': 1024 * 1024 * (S_COARSE + S_FINE) / (ms_i * 1e-3) / 1e6}}
+        del rmhd, ren
+
     # ---- density-temperature config (DT_2012_11.yaml: NeRF_DT + AIA response head, 3072 rays, 7 channels, half of the
     #      rays with the STEREO channel mask) - reported next to the headline, same fast path
     del trainer, rend, renderer
@@ -352,20 +383,30 @@ def main():
     e2e = N * world * args.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     achieved = N * FLOP_TRAIN_RAY / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-    traffic = None             # DRAM bytes of the field-network kernels of one step, from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
-    if args.precision == 'bf16' and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('train_step_mlp_traffic_bytes')
+    # DRAM bytes of the field-network kernels of one step: ncu cannot run inside a timed bench, so this is the committed
+    # `ncu --set full` capture of this same command (profiles/r02_ncu_traffic.json, falling back to round 1's)
+    traffic, traffic_src = None, None
+    for name in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', name)
+        if args.precision == 'bf16' and os.path.exists(tpath):
+            traffic, traffic_src = json.load(open(tpath)).get('train_step_mlp_traffic_bytes'), 'profiles/' + name
+            break
+    step_tflops = N * FLOP_TRAIN_RAY / (ms / args.steps * 1e-3) / 1e12
     line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f16 operands (weights, activations, scaled gradients), f32 accumulate' if args.precision == 'bf16' else 'f32',
+            'data': 'synthetic',
             'config': workload_config(world),
             'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches) * world,
             'roofline': {'bound': 'tensor', 'kernel': f'field-network MLP forward+backward ({args.precision})',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
-                         'traffic': traffic, 'peak_source': pk['src'] + ' (sustained cuBLAS bf16: the kernels run inside a long step)',
+                         'traffic': traffic, 'traffic_source': traffic_src,
+                         # the same FLOPs over the HEADLINE step time (graph replay, coarse backward overlapped, every other
+                         # kernel of the step included): the self-consistent whole-step figure
+                         'frac_from_step': step_tflops / pk['tflops'], 'achieved_from_step': step_tflops,
+                         'peak_source': pk['src'] + ' (sustained cuBLAS bf16: the kernels run inside a long step)',
                          'launches_per_step': 6 if args.precision == 'bf16' else None, 'kernels': kernels,
                          'forward': {'ms_per_step': fwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_FWD_POINT / (fwd_ms * 1e-3) / 1e12},
                          'backward': {'ms_per_step': bwd_ms, 'tflops': N * (S_COARSE + S_FINE) * FLOP_BWD_POINT / (bwd_ms * 1e-3) / 1e12},
@@ -382,6 +423,9 @@ def main():
                        'image_1024': {'ms': ms_image, 'Msamples_per_s': 1024 * 1024 * (S_COARSE + S_FINE) / (ms_image * 1e-3) / 1e6,
                                       'what': 'ObserverRenderer.render_observer_image, 1024x1024 pixels, rays generated on the '
                                               'device, rows sharded over ranks, no collective'}},
+            'render_mhd': {'workload': 'render_mhd.yaml: density-temperature head, C=6, F=1e10, hierarchical sampling on; per field a '
+                                       '4096-ray batch (ms per batch) and ObserverRenderer.render_observer_image at 1024x1024',
+                           **mhd},
             'dt_train': {'workload': 'DT_2012_11.yaml: density-temperature SuNeRF train step, 3072 rays/GPU, C=7 (half STEREO-masked)',
                          'rays_per_s': Nd * world / (ms_dt * 1e-3), 'ms_per_step': ms_dt},
             'clocks': clk}

@@ -7,8 +7,9 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch), unless it says "host";
- *   - every entry is stream-ordered on `stream` (a cudaStream_t), never synchronises, keeps no
- *     pointer after return, allocates nothing and is safe to call from several host threads;
+ *   - every entry is stream-ordered on `stream` (a cudaStream_t) of the CURRENT device, never synchronises, keeps no
+ *     pointer after return, allocates nothing and is safe to call from several host threads and on several devices
+ *     of one process (per-device one-time setup is internal and thread-safe; there is no other mutable state);
  *   - return value: 0 ok, <0 bad argument (SNF_E_*), >0 a cudaError_t;
  *   - float32 everywhere unless a name says bf16; tensors are contiguous row-major.
  */
@@ -73,9 +74,12 @@ int snf_mlp_fwd_f32(const float *x /*[M,4]*/, int64_t M, const float *const *W, 
 int snf_mlp_bwd_f32(const float *x, int64_t M, const float *const *W, int n_hidden, int d_filter,
                     const float *grad_out /*[M,2]*/, void *ws, float *const *gW, float *const *gB, void *stream);
 
-/* bf16 tensor-core entry points (tcgen05 + TMEM, weights streamed by TMA bulk copies).  d_filter==512,
- * n_hidden==8 only.  `packed`: snf_mlp_pack_bytes() bytes holding the bf16 UMMA-layout copy of the weights;
- * repack!=0 re-converts from W/B first (call with repack=1 whenever the fp32 weights changed). */
+/* 16-bit tensor-core entry points ("bf16-MLP mode" of the task; tcgen05 + TMEM, weights streamed by TMA bulk copies).
+ * Operands are fp16 since round 2 (weights, activations, scaled gradients; fp32 accumulation): the 1e-3 per-parameter
+ * gradient gate needs 11-bit significands on the weights.  Raw coordinates must be finite and
+ * below 65504 in magnitude.  d_filter==512, n_hidden==8 only.  `packed`: snf_mlp_pack_bytes() bytes, 1024-byte aligned,
+ * holding the UMMA-layout fp16 copy of the weights; call snf_mlp_pack_bf16 whenever the fp32 weights changed.
+ * ws (train): snf_mlp_ws_bytes(M, 8, 512, 1, 1) bytes, 1024-byte aligned. */
 int64_t snf_mlp_pack_bytes(void);
 int snf_mlp_pack_bf16(const float *const *W, const float *const *B, void *packed, void *stream);
 int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, float out_offset0, float out_offset1,
@@ -179,15 +183,6 @@ int snf_render_fused_bwd(const snf_render_desc *desc, const float *rays_d, const
                          float *const *gW_coarse, float *const *gB_coarse, float *const *gW_fine, float *const *gB_fine,
                          float *g_log_abs_coarse, float *g_vol_c_coarse, float *g_log_abs_fine, float *g_vol_c_fine,
                          void *stream);
-
-/* Measurement aid (bench.py): per-kernel CUDA-event timing of snf_mlp_bwd_bf16 on its launch stream.
- * snf_debug_time_backward(1) arms it and clears the sums, snf_debug_backward_ms(out[3]) returns the number of timed calls
- * and the summed milliseconds of {dgrad chain, wgrad, output-layer gradient}.  Off by default. */
-int snf_debug_time_backward(int on);
-/* Selects the kernel behind snf_mlp_fwd_bf16(train = 0): 0 = activation operand in shared memory, 1 = in tensor memory
- * (tcgen05 TS form).  Returns the previous value; any other argument only queries. */
-int snf_debug_fwd_variant(int variant);
-int snf_debug_backward_ms(double *out_ms);
 
 #ifdef __cplusplus
 }

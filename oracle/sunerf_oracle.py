@@ -74,10 +74,16 @@ def stratified_sample(rays_o: torch.Tensor, rays_d: torch.Tensor, t_vals: torch.
 # --------------------------------------------------------------------------------------
 # a2  HierarchicalSampler.forward + sample_pdf      sunerf/train/sampling.py:111-169
 # --------------------------------------------------------------------------------------
-def pdf_to_cdf(weights_inner: torch.Tensor) -> torch.Tensor:
-    """sampling.py:134-138: pdf=(w+1e-5)/sum(w+1e-5); cdf=[0, cumsum(pdf)]."""
+def pdf_to_cdf(weights_inner: torch.Tensor, exact_sum: bool = False) -> torch.Tensor:
+    """sampling.py:134-138: pdf=(w+1e-5)/sum(w+1e-5); cdf=[0, cumsum(pdf)].
+
+    `torch.sum` is the ONE platform-dependent quantity of the path: on CPU it is a cascade whose grouping follows the
+    vector width of the build, so its last bit differs between CPUs - and from any GPU.
+    exact_sum=True (tests only: tie analysis) replaces it by the exactly rounded sum, which is what the CUDA
+    resampler computes; everything else is unchanged."""
     w = weights_inner + 1e-5
-    pdf = w / torch.sum(w, -1, keepdim=True)
+    norm = w.double().sum(-1, keepdim=True).float() if exact_sum else torch.sum(w, -1, keepdim=True)
+    pdf = w / norm
     cdf = torch.cumsum(pdf, dim=-1)
     return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
 
@@ -103,10 +109,10 @@ def invert_cdf(bins: torch.Tensor, cdf: torch.Tensor, u: torch.Tensor) -> Tuple[
 
 
 def hier_resample(rays_o, rays_d, z_vals, weights, n_new: int = 128,
-                  cdf_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                  cdf_override: Optional[torch.Tensor] = None, exact_sum: bool = False) -> Dict[str, torch.Tensor]:
     """sampling.py:111-126 with perturb=False (:141-143): u = linspace(0,1,n_new)."""
     bins = .5 * (z_vals[..., 1:] + z_vals[..., :-1])                 # :118
-    cdf = pdf_to_cdf(weights[..., 1:-1]) if cdf_override is None else cdf_override
+    cdf = pdf_to_cdf(weights[..., 1:-1], exact_sum) if cdf_override is None else cdf_override
     u = torch.linspace(0., 1., n_new)
     new_z, inds = invert_cdf(bins, cdf, u)
     new_z = new_z.detach()                                           # :120
@@ -338,12 +344,12 @@ def _composite(cfg, p, raw, z, rays_d, wavelengths):
 
 
 def render(cfg: RenderConfig, coarse: FieldParams, fine: FieldParams, rays_o, rays_d, times,
-           wavelengths=None, t_rand=None, keep_intermediates: bool = False) -> Dict[str, torch.Tensor]:
+           wavelengths=None, t_rand=None, keep_intermediates: bool = False, exact_sum: bool = False) -> Dict[str, torch.Tensor]:
     s = stratified_sample(rays_o, rays_d, cfg.t_vals, t_rand, cfg.distance, cfg.solar_R)   # :59
     z = s['z_vals']
     raw_c = _eval_field(cfg, coarse, s['points'], times)
     c_out = _composite(cfg, coarse, raw_c, z, rays_d, wavelengths)                         # :68-71
-    h = hier_resample(rays_o, rays_d, z, c_out['weights'], cfg.n_hier)                      # :76
+    h = hier_resample(rays_o, rays_d, z, c_out['weights'], cfg.n_hier, exact_sum=exact_sum)  # :76
     raw_f = _eval_field(cfg, fine, h['points'], times)
     f_out = _composite(cfg, fine, raw_f, h['z_vals'], rays_d, wavelengths)                  # :86-89
     q = f_out['regularizing_quantity']

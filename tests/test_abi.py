@@ -11,6 +11,7 @@ from conftest import ROOT
 
 def _declared():
     src = open(os.path.join(ROOT, 'include', 'sunerf_b200.h')).read()
+    src += open(os.path.join(ROOT, 'include', 'sunerf_b200_debug.h')).read()      # measurement aids, same library
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(snf_[a-z0-9_]+)\s*\(', src)))
 

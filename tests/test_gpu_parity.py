@@ -3,7 +3,11 @@ the golden vectors generated from the reference.  Tolerances follow BASELINE.jso
   * resampler bin indices: bit-exact at the (cdf,u)->inds stage
   * sampling positions: bit-exact (same fp32 op order, no FMA contraction)
   * rendered intensities: 1e-5 relative in fp32 mode, 1e-2 relative in bf16-MLP mode
-  * per-parameter gradients: 1e-3 relative (fp32 mode; measured as ||g-g_ref||/||g_ref|| per parameter tensor)
+  * per-parameter gradients: 1e-3 relative in BOTH modes, measured as ||g-g_ref||_2/||g_ref||_2 over each FULL parameter
+    tensor against the oracle's autograd gradients computed on the fly (tests/test_gpu_config_scale.py repeats this at
+    the configs' ray counts)
+No multipliers on these gates.  Where a check is not one of north_star's gates (continuity of resampled depths at CDF
+ties, weights/absorption maps) its bound is derived next to it.
 """
 import numpy as np
 import pytest
@@ -63,10 +67,11 @@ def test_resampler_end_to_end():
         uu = u.cpu()[cols]
         lo = torch.minimum(inds[rows, cols], ref[rows, cols])
         assert ((cdf_ref[rows, lo] - uu).abs() <= 2.4e-7).all()
-    assert (new_z.cpu() - torch.from_numpy(g['new_z'])).abs().max() <= 1e-4     # z ~ 215: 1e-4 is ~6 ulp
+    # an index flip at a tie selects the same bin edge: the positions stay continuous, within 2 ulp of z ~ 215 (3.05e-5)
+    assert (new_z.cpu() - torch.from_numpy(g['new_z'])).abs().max() <= 3.06e-5
     zc = z_comb.cpu()
     assert bool((zc[:, 1:] >= zc[:, :-1]).all())
-    assert (zc - torch.from_numpy(g['z_comb'])).abs().max() <= 1e-4
+    assert (zc - torch.from_numpy(g['z_comb'])).abs().max() <= 3.06e-5
 
 
 def test_resampler_unsorted_input_falls_back_to_full_sort():
@@ -99,7 +104,8 @@ def test_field_network_forward(precision, tol):
         y_dt = net_dt(x)['inferences']
     # raw outputs feed exp(): an absolute error e in raw is a relative error e in intensity
     assert (y.cpu() - torch.from_numpy(g['y'])).abs().max() <= tol, (y.cpu() - torch.from_numpy(g['y'])).abs().max()
-    assert (y_dt.cpu() - torch.from_numpy(g['y_dt'])).abs().max() <= tol * 2
+    # the +10 / +5 offsets put y_dt at ~10: one float32 ulp there is 9.5e-7, so the 1e-5 absolute gate still has room
+    assert (y_dt.cpu() - torch.from_numpy(g['y_dt'])).abs().max() <= tol
 
 
 def test_field_network_ragged_and_empty():
@@ -115,29 +121,6 @@ def test_field_network_ragged_and_empty():
             assert (y - orc.field_mlp(x, ref)).abs().max() <= (INT_TOL_F32 if precision == 'fp32' else INT_TOL_BF16)
         with torch.no_grad():
             assert net(torch.zeros(0, 4).cuda())['inferences'].shape == (0, 2)
-
-
-def test_field_network_forward_tmem_operand_variant():
-    """The alternative inference kernel with the activation operand in tensor memory (snf_debug_fwd_variant(1)): same
-    accumulation order as the default kernel, so the two agree to the summation order of the output layer."""
-    import sunerf_b200 as s
-    net, _ = _nets(3)
-    net.cuda()
-    net.precision = 'bf16'
-    ref = oracle_params(net)
-    try:
-        for M in (1, 127, 300, 4096):
-            x = torch.randn(M, 4, generator=torch.Generator().manual_seed(M))
-            s.ops.fwd_variant(0)
-            with torch.no_grad():
-                y_ss = net(x.cuda())['inferences'].cpu()
-            s.ops.fwd_variant(1)
-            with torch.no_grad():
-                y_ts = net(x.cuda())['inferences'].cpu()
-            assert (y_ts - y_ss).abs().max() <= 1e-6
-            assert (y_ts - orc.field_mlp(x, ref)).abs().max() <= INT_TOL_BF16
-    finally:
-        s.ops.fwd_variant(0)
 
 
 def test_simple_star():
@@ -313,7 +296,7 @@ def test_emission_render_drop_in(precision, tol):
                                'height_map', 'absorption_map', 'regularization'}
     _exact(out['z_vals_stratified'], g['out.z_vals_stratified'])
     assert rel_err(out['coarse_image'], g['out.coarse_image']) <= tol
-    assert rel_err(out['fine_image'], g['out.fine_image']) <= (tol if precision == 'bf16' else 2 * tol)
+    assert rel_err(out['fine_image'], g['out.fine_image']) <= tol
     assert out['fine_image'].shape == (g['rays_o'].shape[0], 1)
     assert (out['z_vals_hierarchical'].cpu() - torch.from_numpy(g['out.z_vals_hierarchical'])).abs().max() <= (2e-4 if precision == 'fp32' else 5e-2)
     if precision == 'fp32':
@@ -334,8 +317,7 @@ def test_dt_render_drop_in():
         out = r(t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['wavelengths']), t_rand=t(g['t_rand']))
     for k in ('coarse_image', 'fine_image'):
         ref = torch.from_numpy(g['out.' + k])
-        # DT intensities are exp(2*ln rho): an fp32 GEMM-order difference of 1e-6 in the raw outputs is 2e-6 here
-        assert ((out[k].cpu() - ref).abs() <= 4 * INT_TOL_F32 * ref.abs() + 1e-12).all(), rel_err(out[k], ref, 1e-9)
+        assert ((out[k].cpu() - ref).abs() <= INT_TOL_F32 * ref.abs() + 1e-12).all(), rel_err(out[k], ref, 1e-9)
 
 
 def test_simple_star_render_drop_in():
@@ -347,27 +329,70 @@ def test_simple_star_render_drop_in():
             for i, c in enumerate(orc.AIA_CHANNELS):
                 m.log_absortpion[str(c)].fill_(float(g['log_abs'][i]))
         out = r(t(g['rays_o']), t(g['rays_d']), t(g['times']), t(g['wavelengths']), t_rand=t(g['t_rand']))
-    for k in ('coarse_image', 'fine_image'):
-        ref = torch.from_numpy(g['out.' + k])
-        assert ((out[k].cpu() - ref).abs() <= 2e-5 * ref.abs() + 1e-30).all(), rel_err(out[k], ref, 1e-20)
+    ref = torch.from_numpy(g['out.coarse_image'])
+    assert ((out['coarse_image'].cpu() - ref).abs() <= INT_TOL_F32 * ref.abs() + 1e-30).all(), rel_err(out['coarse_image'], ref, 1e-20)
+    # Fine pass.  The resampler's normaliser sum(w + 1e-5) is the ONE platform-dependent quantity of the path (torch's CPU
+    # cascade sum): where it differs in the last bit a CDF tie flips, a resampled depth moves by one ulp of
+    # z ~ 215, and behind this field's step at the photosphere that is up to 5e-5 of the pixel.  So: every pixel outside
+    # the gate must be such a ray, and against the oracle with the exactly rounded normaliser every pixel is inside.
+    ref = torch.from_numpy(g['out.fine_image'])
+    outside = ((out['fine_image'].cpu() - ref).abs() > INT_TOL_F32 * ref.abs() + 1e-30).any(-1)
+    moved = (out['z_vals_hierarchical'].cpu() != torch.from_numpy(g['out.z_vals_hierarchical'])).any(-1)
+    assert bool((moved | ~outside).all()), 'a pixel differs although its resampled depths are identical'
+    la = torch.from_numpy(g['log_abs'])
+    a = golden('aia_response.npz')
+    cfg = orc.RenderConfig(kind='dt', pixel_intensity_factor=1e10, table_x=torch.from_numpy(a['logT']), table_y=torch.from_numpy(a['table']),
+                           field='simple_star')
+    pp = orc.FieldParams([], [], la, torch.tensor(1.0))
+    with torch.no_grad():
+        ex = orc.render(cfg, pp, pp, *(torch.from_numpy(g[k]) for k in ('rays_o', 'rays_d', 'times', 'wavelengths', 't_rand')),
+                        exact_sum=True)
+    assert ((out['fine_image'].cpu() - ex['fine_image']).abs() <= INT_TOL_F32 * ex['fine_image'].abs() + 1e-30).all(), \
+        rel_err(out['fine_image'], ex['fine_image'], 1e-20)
 
 
 # ------------------------------------------------------------------------------------------ a11/a12 training
-def _grad_checks(g, prefix, model):
-    worst = 0.0
-    for name, p in model.named_parameters():
-        key = f'{prefix}.{name}'
-        gn_ref = float(g[key + '.gnorm'])
-        gr = p.grad if p.grad is not None else torch.zeros_like(p)
-        gn = gr.double().norm().item()
-        assert abs(gn - gn_ref) <= GRAD_TOL * gn_ref + 1e-12, (key, gn, gn_ref)
-        if key + '.gslice' in g.files:
-            from oracle.make_golden import GRAD_SLICES
-            sl = gr[GRAD_SLICES[name]].cpu()
-            ref = torch.from_numpy(g[key + '.gslice'])
-            e = ((sl - ref).norm() / ref.norm()).item()
-            worst = max(worst, e)
-            assert e <= GRAD_TOL, (key, e)
+def _oracle_step(kind, g, r):
+    """The oracle's training step (forward, loss, autograd backward) on the golden inputs with the module's weights:
+    loss and EVERY parameter gradient in full, keyed like model.named_parameters()."""
+    dt = kind == 'dt'
+    pc, pf = oracle_params(r.coarse_model, dt).requires_grad_(), oracle_params(r.fine_model, dt).requires_grad_()
+    if dt:
+        a = golden('aia_response.npz')
+        cfg = orc.RenderConfig(kind='dt', pixel_intensity_factor=float(r.pixel_intensity_factor),
+                               table_x=torch.from_numpy(a['logT']), table_y=torch.from_numpy(a['table']))
+        wl = torch.from_numpy(g['wavelengths'])
+    else:
+        cfg, wl = orc.RenderConfig(kind='emission'), None
+    out = orc.render(cfg, pc, pf, torch.from_numpy(g['rays_o']), torch.from_numpy(g['rays_d']), torch.from_numpy(g['times']), wl,
+                     torch.from_numpy(g['t_rand']))
+    losses = orc.training_loss(out, torch.from_numpy(g['target']), kind)
+    losses['loss'].backward()
+    names = ['in_layer.1'] + [f'layers.{i}' for i in range(len(pc.weights) - 2)] + ['out_layer']
+    grads = {}
+    for prefix, p in (('coarse_model', pc), ('fine_model', pf)):
+        for n, w, b in zip(names, p.weights, p.biases):
+            grads[f'{prefix}.{n}.weight'], grads[f'{prefix}.{n}.bias'] = w.grad, b.grad
+        if dt:
+            grads[f'{prefix}.log_absortpion'], grads[f'{prefix}.volumetric_constant'] = p.log_abs.grad, p.vol_c.grad
+    return losses['loss'].item(), grads, out
+
+
+def _grad_checks(r, ref_grads, dt=False):
+    """||g - g_ref||_2 / ||g_ref||_2 <= 1e-3 for every parameter tensor, in full. Returns the worst (name, error)."""
+    worst = ('', 0.0)
+    for prefix in ('coarse_model', 'fine_model'):
+        model = getattr(r, prefix)
+        got = {n: p.grad for n, p in model.named_parameters() if not n.startswith('log_absortpion')}
+        if dt:
+            got['log_absortpion'] = torch.stack([model.log_absortpion[str(c)].grad for c in orc.AIA_CHANNELS])
+        for n, gr in got.items():
+            ref = ref_grads[f'{prefix}.{n}']
+            assert gr is not None and gr.shape == ref.shape, (prefix, n)
+            e = ((gr.detach().cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+            if e > worst[1]:
+                worst = (f'{prefix}.{n}', e)
+            assert e <= GRAD_TOL, (prefix, n, e)
     return worst
 
 
@@ -382,13 +407,14 @@ def test_emission_training_gradients_autograd():
     loss = mse(scal(out['coarse_image']), tgt) + mse(scal(out['fine_image']), tgt) + out['regularization'].mean()
     assert abs(loss.item() - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
     loss.backward()
-    _grad_checks(g, 'coarse_model', r.coarse_model)
-    _grad_checks(g, 'fine_model', r.fine_model)
+    ref_loss, ref_grads, _ = _oracle_step('emission', g, r)
+    assert abs(ref_loss - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))      # the oracle run here == the pinned golden
+    print('fp32 worst full-tensor gradient error', _grad_checks(r, ref_grads))
 
 
 def test_emission_training_gradients_bf16():
-    """bf16 tensor-core mode (tcgen05 forward, dgrad chain and MN-major wgrad): loss within 1e-2, per-parameter
-    gradient tensors within 5e-2 of the fp32 reference gradients (bf16 operands carry 2^-9 relative rounding)."""
+    """Tensor-core mode (tcgen05 forward, dgrad chain and MN-major wgrad, fp16 operands): loss within 1e-2, EVERY
+    parameter gradient tensor within 1e-3 of the oracle's fp32 autograd gradients (north_star's gate, no multiplier)."""
     import sunerf_b200 as s
     g, r = _emission_module('bf16')
     out = r(t(g['rays_o']), t(g['rays_d']), t(g['times']), t_rand=t(g['t_rand']))
@@ -398,20 +424,8 @@ def test_emission_training_gradients_bf16():
     loss = mse(scal(out['coarse_image']), tgt) + mse(scal(out['fine_image']), tgt) + out['regularization'].mean()
     assert abs(loss.item() - float(g['loss'])) <= INT_TOL_BF16 * abs(float(g['loss']))
     loss.backward()
-    from oracle.make_golden import GRAD_SLICES
-    worst = 0.0
-    for prefix, model in (('coarse_model', r.coarse_model), ('fine_model', r.fine_model)):
-        for name, p in model.named_parameters():
-            key = f'{prefix}.{name}'
-            ref = float(g[key + '.gnorm'])
-            got = p.grad.double().norm().item()
-            assert abs(got - ref) <= 5e-2 * ref, (key, got, ref)
-            if key + '.gslice' in g.files:
-                sl, rs = p.grad[GRAD_SLICES[name]].cpu(), torch.from_numpy(g[key + '.gslice'])
-                e = ((sl - rs).norm() / rs.norm()).item()
-                worst = max(worst, e)
-                assert e <= 5e-2, (key, e)
-    print('bf16 worst gradient-slice relative error', worst)
+    _, ref_grads, _ = _oracle_step('emission', g, r)
+    print('tensor-core mode worst full-tensor gradient error', _grad_checks(r, ref_grads))
 
 
 def test_ray_trainer_bf16_matches_fp32():
@@ -423,9 +437,9 @@ def test_ray_trainer_bf16_matches_fp32():
     a = t32.step(*args, t_rand=t(g['t_rand']))
     b = t16.step(*args, t_rand=t(g['t_rand']))
     assert abs(a['losses'][0].item() - b['losses'][0].item()) <= INT_TOL_BF16 * abs(a['losses'][0].item())
-    assert abs(a['grad_norm'].item() - b['grad_norm'].item()) <= 5e-2 * a['grad_norm'].item()
-    cos = torch.nn.functional.cosine_similarity(t32.flat_grad.double(), t16.flat_grad.double(), dim=0).item()
-    assert cos > 0.998, cos
+    assert abs(a['grad_norm'].item() - b['grad_norm'].item()) <= GRAD_TOL * a['grad_norm'].item()
+    rel = ((t32.flat_grad.double() - t16.flat_grad.double()).norm() / t32.flat_grad.double().norm()).item()
+    assert rel <= GRAD_TOL, rel
     # a second step runs on refreshed packed weights
     b2 = t16.step(*args, t_rand=t(g['t_rand']))
     assert torch.isfinite(b2['losses']).all()
@@ -446,8 +460,8 @@ def test_dt_training_gradients_autograd():
     loss = mse(out['coarse_image'], t(g['target'])) + mse(out['fine_image'], t(g['target'])) + out['regularization'].mean()
     assert abs(loss.item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
     loss.backward()
-    _grad_checks(g, 'coarse_model', r.coarse_model)
-    _grad_checks(g, 'fine_model', r.fine_model)
+    _, ref_grads, _ = _oracle_step('dt', g, r)
+    print('DT fp32 worst full-tensor gradient error', _grad_checks(r, ref_grads, dt=True))
 
 
 def test_dt_ray_trainer_bf16_matches_fp32():
@@ -470,11 +484,11 @@ def test_dt_ray_trainer_bf16_matches_fp32():
     a16 = trainers[1].step(*args, t_rand=t(g['t_rand']))
     assert abs(a32['losses'][0].item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
     ref = a32['fine_image']
-    # exp(2 ln rho) doubles the relative error of the raw outputs: 2e-2 on the DT intensities in bf16 mode
-    assert ((a16['fine_image'] - ref).abs() <= 2 * INT_TOL_BF16 * ref.abs() + 1e-12).all()
-    cos = torch.nn.functional.cosine_similarity(trainers[0].flat_grad.double(), trainers[1].flat_grad.double(), dim=0).item()
-    assert cos > 0.995, cos
-    assert abs(a32['grad_norm'].item() - a16['grad_norm'].item()) <= 5e-2 * a32['grad_norm'].item()
+    assert ((a16['fine_image'] - ref).abs() <= INT_TOL_BF16 * ref.abs() + 1e-12).all()
+    rel = ((trainers[0].flat_grad.double() - trainers[1].flat_grad.double()).norm() / trainers[0].flat_grad.double().norm()).item()
+    print('DT tensor-core vs fp32 mode, flat gradient relative error', rel)
+    assert rel <= GRAD_TOL, rel
+    assert abs(a32['grad_norm'].item() - a16['grad_norm'].item()) <= GRAD_TOL * a32['grad_norm'].item()
     trainers[1].check_finite()
 
 
@@ -519,9 +533,9 @@ def test_ray_trainer_bf16_ragged_batch_and_padding_tiles():
     t32, t16 = s.RayTrainer(r32), s.RayTrainer(r16)
     a, b = t32.step(*args, t_rand=tr), t16.step(*args, t_rand=tr)
     assert abs(a['losses'][0].item() - b['losses'][0].item()) <= INT_TOL_BF16 * abs(a['losses'][0].item())
-    cos = torch.nn.functional.cosine_similarity(t32.flat_grad.double(), t16.flat_grad.double(), dim=0).item()
-    assert cos > 0.998, cos
-    assert abs(a['grad_norm'].item() - b['grad_norm'].item()) <= 5e-2 * a['grad_norm'].item()
+    rel = ((t32.flat_grad.double() - t16.flat_grad.double()).norm() / t32.flat_grad.double().norm()).item()
+    assert rel <= GRAD_TOL, rel
+    assert abs(a['grad_norm'].item() - b['grad_norm'].item()) <= GRAD_TOL * a['grad_norm'].item()
     t16.check_finite()
 
 
@@ -615,7 +629,11 @@ def test_fused_render_c_entry_matches_the_staged_path_emission(precision):
     # forward-only instance: same images, nothing kept
     with torch.no_grad():
         fo2 = s.FusedRender(r, N).forward(ro, rd, tm, t_rand=tr)
-    _exact(fo2['fine_image'], fo['fine_image'].cpu().numpy())
+    if precision == 'fp32':
+        _exact(fo2['fine_image'], fo['fine_image'].cpu().numpy())
+    else:   # the training forward forms sin(pre) as 2 sin(pre/2) cos(pre/2) (it needs both for the cosine code), the inference
+        # forward as sin(pre): two roundings of the same fp16 activations, far inside the mode's 1e-2 gate
+        assert rel_err(fo2['fine_image'], fo['fine_image']) <= 1e-4
 
 
 def test_fused_render_c_entry_matches_the_staged_path_density_temperature():

@@ -37,6 +37,24 @@ def _write(tmp_path, m, c=1, wl=False):
     return arrs
 
 
+def test_tail_batch_gives_every_rank_a_shard():
+    """A short last batch (here 9 rays over 8 ranks, then 3 over 8) is split evenly: no rank is empty while the batch has
+    at least `world` rays (ceil-sized chunks left trailing ranks with nothing and hung the all-reduce), the shards tile
+    the batch in rank order, and a batch smaller than the world leaves the surplus ranks an EMPTY shard (a no-op step)."""
+    from sunerf_b200.ray_store import RayStore
+    for m, B, world in ((1033, 1024, 8), (1027, 1024, 8), (2048 + 49, 1024, 8), (100, 64, 3)):
+        st = RayStore.__new__(RayStore)                      # the split needs no device
+        st.n_rays, st.batch_size, st.world, st.rank = m, B, world, 0
+        for idx in range(len(st)):
+            lo, hi = idx * B, min((idx + 1) * B, m)
+            rng = [st.shard_range(idx, r) for r in range(world)]
+            assert rng[0][0] == lo and rng[-1][1] == hi
+            assert all(rng[r][1] == rng[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in rng]
+            assert max(sizes) - min(sizes) <= 1
+            assert min(sizes) >= 1 or hi - lo < world
+
+
 @pytest.mark.gpu
 def test_ray_store_batches_equal_mmap_dataset_slices(tmp_path):
     import sunerf_b200 as s
@@ -53,8 +71,8 @@ def test_ray_store_batches_equal_mmap_dataset_slices(tmp_path):
         for key, f in (('time', 'times_batches.npy'), ('target_image', 'images_batches.npy'), ('wavelengths', 'wavelengths_batches.npy')):
             got = torch.cat([p[key] for p in parts]).cpu().numpy()
             assert np.array_equal(got, arrs[f][lo:hi].astype(np.float32))
-        # 'dp' scatter: contiguous ceil-sized chunks
-        assert parts[0]['rays_o'].shape[0] == -(-(hi - lo) // world)
+        # contiguous, even shares (at most one ray apart)
+        assert parts[0]['rays_o'].shape[0] == -(-(hi - lo) // world) and parts[1]['rays_o'].shape[0] == (hi - lo) // world
     # views, not copies
     assert stores[0].batch(0)['rays_o'].data_ptr() == stores[0].data['rays_o'].data_ptr()
     with pytest.raises(IndexError):

@@ -21,6 +21,7 @@ struct ProbeArgs {
   const uint8_t *a_img, *b_img;
   float *d;           // [M][N]
   int mode;           // 0 ss, 1 mn, 2 mn swapped, 3 ts
+  int a_fmt, b_fmt;   // 0 = fp16, 1 = bf16 (kind::f16 operand formats, chosen independently)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
 
   if (tid == 0) {
     if (p.mode == 0 || p.mode == 3) {
-      const uint32_t idesc = idesc_bf16(M, N);
+      const uint32_t idesc = idesc_f16kind(M, N, p.a_fmt, p.b_fmt);
       for (int ks = 0; ks < 2; ++ks)
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint64_t bd = smem_desc(sB + ks * (256 * 128) + k4 * 32, 16, 1024);
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
         }
     } else {
       // MN-major: image = [slab of 64 MN-elements][k line (128 B)] ; one K=16 step = 16 lines = 2 KB
-      const uint32_t idesc = idesc_bf16(M, N, 1, 1);
+      const uint32_t idesc = idesc_f16kind(M, N, p.a_fmt, p.b_fmt, 1, 1);
       const uint32_t lbo_a = p.mode == 1 ? 16384u : 1024u, sbo_a = p.mode == 1 ? 1024u : 16384u;
       const uint32_t lbo_b = p.mode == 1 ? 16384u : 1024u, sbo_b = p.mode == 1 ? 1024u : 16384u;
       for (int k16 = 0; k16 < K / 16; ++k16) {
@@ -104,35 +105,44 @@ static uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 static float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+static uint16_t f2h(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+static float h2f(uint16_t b) { __half h; memcpy(&h, &b, 2); return __half2float(h); }
+static int g_afmt = 1, g_bfmt = 1;
+static uint16_t enc(float f, int fmt) { return fmt ? f2bf(f) : f2h(f); }
+static float dec(uint16_t b, int fmt) { return fmt ? bf2f(b) : h2f(b); }
 
 int main(int argc, char **argv) {
   const char *name = argc > 1 ? argv[1] : "ss";
   int mode = !strcmp(name, "ss") ? 0 : !strcmp(name, "mn") ? 1 : !strcmp(name, "mn2") ? 2 : !strcmp(name, "ts") ? 3 : -1;
   if (mode < 0) { printf("unknown test %s\n", name); return 2; }
+  // optional operand formats: "bf16" (default), "f16", "mixed" (A bf16 x B fp16, the backward kernels' combination)
+  const char *fmt = argc > 2 ? argv[2] : "bf16";
+  if (!strcmp(fmt, "f16")) { g_afmt = 0; g_bfmt = 0; } else if (!strcmp(fmt, "mixed")) { g_afmt = 1; g_bfmt = 0; }
+  else if (!strcmp(fmt, "mixed2")) { g_afmt = 0; g_bfmt = 1; }
   std::vector<float> A(M * K), B(N * K);
   srand(1234);
-  for (auto &v : A) v = bf2f(f2bf((float)(rand() % 2001 - 1000) / 1000.f));
-  for (auto &v : B) v = bf2f(f2bf((float)(rand() % 2001 - 1000) / 1000.f));
+  for (auto &v : A) v = dec(enc((float)(rand() % 2001 - 1000) / 1000.f, g_afmt), g_afmt);
+  for (auto &v : B) v = dec(enc((float)(rand() % 2001 - 1000) / 1000.f, g_bfmt), g_bfmt);
   std::vector<uint8_t> a_img(A_IMG, 0), b_img(B_IMG, 0);
   if (mode == 0 || mode == 3) {
     // K-major: slab ks (64 k), row r, chunk c8 -> sw128 ; B has 256 rows per slab
     for (int r = 0; r < M; ++r) for (int k = 0; k < K; ++k) {
-      uint16_t v = f2bf(A[r * K + k]);
+      uint16_t v = enc(A[r * K + k], g_afmt);
       memcpy(&a_img[(k >> 6) * 16384 + sw128_chunk_off(r, (k & 63) >> 3) + (k & 7) * 2], &v, 2);
     }
     for (int r = 0; r < N; ++r) for (int k = 0; k < K; ++k) {
-      uint16_t v = f2bf(B[r * K + k]);
+      uint16_t v = enc(B[r * K + k], g_bfmt);
       memcpy(&b_img[(k >> 6) * (256 * 128) + sw128_chunk_off(r, (k & 63) >> 3) + (k & 7) * 2], &v, 2);
     }
   } else {
     // MN-major: slab = 64 consecutive m (or n); inside a slab line k holds the 64 values, chunk order swizzled by k%8.
     // This is byte-identical to a K-major image of the TRANSPOSED matrix [k rows][m cols] with 128 rows per slab.
     for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) {
-      uint16_t v = f2bf(A[m * K + k]);
+      uint16_t v = enc(A[m * K + k], g_afmt);
       memcpy(&a_img[(m >> 6) * 16384 + sw128_chunk_off(k, (m & 63) >> 3) + (m & 7) * 2], &v, 2);
     }
     for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {
-      uint16_t v = f2bf(B[n * K + k]);
+      uint16_t v = enc(B[n * K + k], g_bfmt);
       memcpy(&b_img[(n >> 6) * 16384 + sw128_chunk_off(k, (n & 63) >> 3) + (n & 7) * 2], &v, 2);
     }
   }
@@ -143,7 +153,7 @@ int main(int argc, char **argv) {
   cudaMemset(dd, 0, M * N * 4);
   const int smem = A_IMG + B_IMG + 1024 + 64;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  ProbeArgs p{da, db, dd, mode};
+  ProbeArgs p{da, db, dd, mode, g_afmt, g_bfmt};
   probe_kernel<<<1, 128, smem>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("PROBE %s: CUDA error %s\n", name, cudaGetErrorString(e)); return 1; }
@@ -157,7 +167,7 @@ int main(int argc, char **argv) {
     if (err > maxerr) maxerr = err;
     if (err > 1e-3) ++bad;
   }
-  printf("PROBE %s: max abs err %.3e, mismatches %d / %d -> %s\n", name, maxerr, bad, M * N, bad == 0 ? "PASS" : "FAIL");
+  printf("PROBE %s/%s: max abs err %.3e, mismatches %d / %d -> %s\n", name, fmt, maxerr, bad, M * N, bad == 0 ? "PASS" : "FAIL");
   if (bad) {
     printf("  D[0][0..7]  :"); for (int i = 0; i < 8; ++i) printf(" %8.4f", D[i]); printf("\n  ref[0][0..7]:");
     for (int n = 0; n < 8; ++n) { double r = 0; for (int k = 0; k < K; ++k) r += (double)A[k] * B[n * K + k]; printf(" %8.4f", r); }
