@@ -4,7 +4,7 @@ Drop-in surface (same names, constructor arguments, forward contracts and state_
 
     sunerf/model/model.py            -> sunerf_b200.model      NeRF, NeRF_DT, EmissionModel, PositionalEncoding, Sine
     sunerf/model/stellar_model.py    -> sunerf_b200.model      SimpleStar
-    sunerf/train/sampling.py         -> sunerf_b200.sampling   StratifiedSampler, HierarchicalSampler
+    sunerf/train/sampling.py         -> sunerf_b200.sampling   StratifiedSampler, SphericalSampler, HierarchicalSampler
     sunerf/rendering/*.py            -> sunerf_b200.rendering  SuNeRFRendering, EmissionRadiativeTransfer,
                                                                DensityTemperatureRadiativeTransfer
     sunerf/train/scaling.py          -> sunerf_b200.trainer    ImageAsinhScaling
@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import SnfError, build
 from . import ops
 from .model import NeRF, NeRF_DT, EmissionModel, PositionalEncoding, Sine, SimpleStar
-from .sampling import StratifiedSampler, HierarchicalSampler
+from .sampling import StratifiedSampler, SphericalSampler, HierarchicalSampler
 from .rendering import SuNeRFRendering, EmissionRadiativeTransfer, DensityTemperatureRadiativeTransfer
 from .trainer import RayTrainer, ImageAsinhScaling
 from . import rays, parallel, image_render, checkpoint, ray_store
@@ -28,5 +28,5 @@ from .image_render import ObserverRenderer
 from .fused import FusedRender
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
-           'StratifiedSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
+           'StratifiedSampler', 'SphericalSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
            'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore', 'FusedRender']

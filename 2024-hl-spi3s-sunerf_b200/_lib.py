@@ -73,7 +73,9 @@ _PROTOS = {
     'snf_launch_count': (_L, []),
     'snf_count_launches': (None, [_L]),
     'snf_stratified_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
+    'snf_spherical_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
     'snf_hier_resample': (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
+    'snf_hier_resample_perturb': (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
     'snf_image_rays': (_I, [_P, _I, _I, _D, _D, _D, _D, _L, _L, _P, _P, _P]),
     'snf_make_query': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     'snf_mlp_ws_bytes': (_L, [_L, _I, _I, _I, _I]),

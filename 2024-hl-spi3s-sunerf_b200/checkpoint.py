@@ -18,6 +18,7 @@ from typing import Any, Dict, Optional
 import torch
 from torch import nn
 
+from . import ops
 from ._lib import SnfError
 from .model import NeRF, NeRF_DT, SimpleStar
 from .rendering import DensityTemperatureRadiativeTransfer, EmissionRadiativeTransfer, SuNeRFRendering
@@ -67,17 +68,29 @@ class _Opaque:
 _OPAQUE: Dict[str, type] = {}
 
 
+# What a reference save_state.snf legitimately pickles: tensors / storages / nn modules (torch), containers
+# (collections), numpy arrays and scalars of the data config, datetimes, and a handful of harmless builtins.  Every other
+# global the pickle names - whether its package is installed here or not - becomes an inert _Opaque stand-in: it is
+# never imported and none of its code runs.  (A pickle is still a program: load files from sources you trust.)
+_ALLOWED_ROOTS = ('torch', 'collections', 'numpy', 'datetime', '_codecs', 'copyreg', 'sunerf_b200')
+_ALLOWED_BUILTINS = {'set', 'frozenset', 'slice', 'complex', 'dict', 'list', 'tuple', 'int', 'float', 'str', 'bool', 'bytes',
+                     'bytearray', 'range', 'object', 'getattr'}
+
+
 class _RefUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == 'sunerf' or module.startswith('sunerf.'):
             return _stub_for(module, name)
-        try:
-            return super().find_class(module, name)
-        except (ImportError, AttributeError):
-            key = f'{module}.{name}'
-            if key not in _OPAQUE:
-                _OPAQUE[key] = type(name, (_Opaque,), {'_ref_name': key})
-            return _OPAQUE[key]
+        root = module.split('.')[0]
+        if root in _ALLOWED_ROOTS or (module in ('builtins', '__builtin__') and name in _ALLOWED_BUILTINS and name != 'getattr'):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                pass
+        key = f'{module}.{name}'
+        if key not in _OPAQUE:
+            _OPAQUE[key] = type(name, (_Opaque,), {'_ref_name': key})
+        return _OPAQUE[key]
 
 
 class _RefPickle:
@@ -105,15 +118,54 @@ def _model_class_and_config(stub_model: nn.Module):
     raise SnfError(f'unknown field-network class in the pickle: {name}')
 
 
+def _tensors_in(obj, depth: int = 0):
+    """every tensor reachable through the attributes of an (opaque) unpickled object"""
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif depth < 4:
+        vals = obj.values() if isinstance(obj, dict) else (obj if isinstance(obj, (list, tuple)) else
+                                                           getattr(obj, '__dict__', {}).values())
+        for v in vals:
+            yield from _tensors_in(v, depth + 1)
+
+
+def _adopt_pickled_response(stub: nn.Module, rend: DensityTemperatureRadiativeTransfer) -> None:
+    """The reference does not store `aia_exp_time`; what it pickles are the interpolators of `self.response`
+    (density_temperature.py:144-146), whose y tables are float32(TRESP * aia_exp_time).  A model trained with another
+    exposure time must render with ITS tables, not with the shipped 2.9 s ones: take them from the pickle when they can
+    be found there (7 channels x 101 values on the shipped logT grid), otherwise say that the shipped table is used."""
+    resp = getattr(stub, 'response', None)
+    if not isinstance(resp, dict):
+        return
+    tx, ty = rend._table_x, rend._table_y.clone()
+    found = 0
+    for i, ch in enumerate(ops.AIA_CHANNELS):
+        interp = resp.get(ch, resp.get(str(ch), resp.get(float(ch))))
+        cands = [t.detach().float().reshape(-1) for t in _tensors_in(interp) if t.numel() == tx.numel()]
+        ys = [t for t in cands if not torch.equal(t, tx) and float(t.abs().max()) < 1.0]     # responses are ~1e-24, logT is 4..9
+        if len(ys) == 1:
+            ty[i] = ys[0]
+            found += 1
+    if found == len(ops.AIA_CHANNELS):
+        rend._table_y.copy_(ty)
+    elif found:
+        raise SnfError('only some of the pickled AIA response tables could be recovered: refusing to mix them with the shipped ones')
+    else:
+        import warnings
+        warnings.warn('the pickled response interpolators carry no recoverable tables (xitorch layout unknown): rendering with '
+                      'the shipped aia_exp_time = 2.9 s response; pass aia_exp_time explicitly if the model was trained otherwise')
+
+
 def rebuild_rendering(stub: nn.Module, precision: Optional[str] = None) -> SuNeRFRendering:
     """A rendering module of this package with the structure and weights of an unpickled reference module."""
     name = type(stub).__name__
     Rs = float(stub.Rs_per_ds)
     smp, hs = stub.sampler, stub.sampler_hierarchical
-    if type(smp).__name__ != 'StratifiedSampler':
-        raise SnfError(f'{type(smp).__name__} is outside the hot path (only StratifiedSampler is built)')
-    sampling_config = {'type': 'stratified', 'distance': float(smp.distance) * Rs, 'n_samples': int(smp.t_vals.shape[-1]),
-                       'perturb': bool(smp.perturb)}
+    kinds = {'StratifiedSampler': 'stratified', 'SphericalSampler': 'spherical'}
+    if type(smp).__name__ not in kinds:
+        raise SnfError(f'unknown sampler class in the pickle: {type(smp).__name__}')
+    sampling_config = {'type': kinds[type(smp).__name__], 'distance': float(smp.distance) * Rs,
+                       'n_samples': int(smp.t_vals.shape[-1]), 'perturb': bool(smp.perturb)}
     hier_config = {'type': 'hierarchical', 'n_samples': int(hs.n_samples), 'perturb': bool(hs.perturb)}
     model_cls, model_cfg = _model_class_and_config(stub.fine_model)
     if precision is not None and model_cls is not SimpleStar:
@@ -126,8 +178,8 @@ def rebuild_rendering(stub: nn.Module, precision: Optional[str] = None) -> SuNeR
         rend = DensityTemperatureRadiativeTransfer(Rs_per_ds=Rs, sampling_config=sampling_config,
                                                    hierarchical_sampling_config=hier_config, model=model_cls,
                                                    model_config=model_cfg,
-                                                   pixel_intensity_factor=float(getattr(stub, 'pixel_intensity_factor', 1e10)),
-                                                   aia_exp_time=float(getattr(stub, 'aia_exp_time', 2.9)))
+                                                   pixel_intensity_factor=float(getattr(stub, 'pixel_intensity_factor', 1e10)))
+        _adopt_pickled_response(stub, rend)
     else:
         raise SnfError(f'unknown rendering class in the pickle: {name}')
     sd = {k: v for k, v in stub.state_dict().items() if k in rend.state_dict()}

@@ -1,5 +1,6 @@
 // Ray-sample placement kernels (HBM-bound, fp32 with the reference's exact operation order).
 //   K1 stratified_kernel : StratifiedSampler.forward      sunerf/train/sampling.py:68-102
+//                          SphericalSampler.forward       sunerf/train/sampling.py:16-54 (same kernel, other bin ends)
 //   K2 hier_kernel       : HierarchicalSampler.forward    sunerf/train/sampling.py:111-169
 //   make_query_kernel    : o + d*z, cat time              sampling.py:100, base_tracing.py:64-65
 #include "snf_common.cuh"
@@ -20,7 +21,8 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
                                                          const float *__restrict__ t_vals,
                                                          const float *__restrict__ t_rand, int64_t N, int S,
                                                          float D, float solar_R, float *__restrict__ z_out,
-                                                         float *__restrict__ pts_out, int rpw /* rays per warp, <= 32 */) {
+                                                         float *__restrict__ pts_out, int rpw /* rays per warp, <= 32 */,
+                                                         int spherical) {
   const int lane = threadIdx.x & 31;
   const int64_t ray0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw;
   if (ray0 >= N) return;
@@ -34,9 +36,15 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
   const float qc = fsub(osq, fmul(solar_R, solar_R));                             // :80
   const float disc = fsub(fmul(qb, qb), fmul(fmul(4.f, qa), qc));
   const float hit = fdiv(fsub(-qb, __fsqrt_rn(disc)), fmul(2.f, qa));             // :81 (NaN on a miss)
-  const float my_near = fsub(r_obs, D);                                           // :83
+  float my_near = fsub(r_obs, D);                                                 // :83
   float my_far = fadd(r_obs, D);                                                  // :84
-  if (hit == hit) my_far = hit;                                                   // :87-88
+  if (spherical) {   // SphericalSampler: entry / exit of the sphere of radius D (sampling.py:26-30; NaN when the ray misses it)
+    const float qcd = fsub(osq, fmul(D, D));
+    const float rt = __fsqrt_rn(fsub(fmul(qb, qb), fmul(fmul(4.f, qa), qcd)));
+    my_near = fdiv(fsub(-qb, rt), fmul(2.f, qa));
+    my_far = fdiv(fadd(-qb, rt), fmul(2.f, qa));
+  }
+  if (hit == hit) my_far = hit;                                                   // :87-88 / :37-38
   const int nr = (int)(N - ray0 < rpw ? N - ray0 : rpw);
   auto do_ray = [&](int r, const float (&tr)[NJ > 0 ? NJ : 1]) {
     const float z_near = __shfl_sync(kFull, my_near, r), z_far = __shfl_sync(kFull, my_far, r);
@@ -129,21 +137,28 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
                                                    const float *__restrict__ u, const float *__restrict__ cdf_in,
                                                    int64_t N, int S, int n_new, float *__restrict__ new_z,
                                                    float *__restrict__ z_comb, int64_t *__restrict__ inds,
-                                                   float *__restrict__ cdf_out) {
+                                                   float *__restrict__ cdf_out, int u_per_ray) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const int T = S + n_new;
   // CTA-wide: the u grid; per warp: zs[S] bins[S] cdf[S] nz[n_new] comb[T] | first[S] a[S] cnt[max(S, n_new) + 2]
+  // (+ u_row[n_new] per warp when every ray has its own draws: HierarchicalSampler(perturb=True), sampling.py:144-146)
   float *us = sm;
-  for (int k = threadIdx.x; k < n_new; k += blockDim.x) us[k] = u[k];
+  if (!u_per_ray)
+    for (int k = threadIdx.x; k < n_new; k += blockDim.x) us[k] = u[k];
   __syncthreads();
   if (ray >= N) return;  // whole warp exits together; only __syncwarp below
   const int ncnt = (S > n_new ? S : n_new) + 2;
-  float *zs = sm + n_new + (size_t)warp * (3 * S + n_new + T + 2 * S + ncnt);
+  const size_t wsz = (size_t)(3 * S + n_new + T + 2 * S + ncnt) + (u_per_ray ? n_new : 0);
+  float *zs = sm + n_new + (size_t)warp * wsz;
   float *bins = zs + S, *cdf = bins + S, *nz = cdf + S, *comb = nz + n_new;
   int *first = reinterpret_cast<int *>(comb + T), *arank = first + S, *cnt = arank + S;
   const int nc = S - 1;  // CDF length == number of bin centres
+  if (u_per_ray) {
+    us = reinterpret_cast<float *>(cnt + ncnt);
+    for (int k = lane; k < n_new; k += 32) us[k] = __ldcs(u + ray * n_new + k);
+  }
 
   for (int j = lane; j < S; j += 32) zs[j] = __ldcs(z_vals + ray * S + j);
   for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;
@@ -171,7 +186,8 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   if (cdf_out != nullptr)
     for (int j = lane; j < nc; j += 32) cdf_out[ray * nc + j] = cdf[j];
 
-  // ---- first[j] = #{k : u_k < cdf_j} and its histogram
+  // ---- first[j] = #{k : u_k < cdf_j} and its histogram (ascending shared u only)
+  if (!u_per_ray)
   for (int j = lane; j < nc; j += 32) {
     const float c = cdf[j];
     int k0 = __float2int_ru(c * (float)(n_new - 1));        // exact on the ideal grid k / (n - 1); NaN -> 0
@@ -184,7 +200,23 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   __syncwarp();
   // ---- inds[k] = #{j : cdf_j <= u_k} (searchsorted right=True, :149) and the inverse-CDF samples
   int ind[PER];
-  warp_prefix_counts<PER>(cnt, n_new, lane, ind);
+  if (!u_per_ray) {
+    warp_prefix_counts<PER>(cnt, n_new, lane, ind);
+  } else {   // unordered per-ray draws: one upper-bound binary search per draw, as torch.searchsorted(right=True) does
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = lane * PER + i;
+      int lo = 0, hi = nc;
+      if (k < n_new) {
+        const float uu = us[k];
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+        }
+      }
+      ind[i] = lo;
+    }
+  }
   __syncwarp();
   for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;         // reused for the merge below
 #pragma unroll
@@ -210,7 +242,7 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   bool sorted = true;
   for (int j = lane; j < S - 1; j += 32) sorted &= (zs[j] <= zs[j + 1]);
   for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
-  sorted = __all_sync(kFull, sorted);
+  sorted = __all_sync(kFull, sorted) && !u_per_ray;        // first[] exists for the shared ascending grid only
   if (sorted) {
     // a[j] = #{k : new_z_k < z_j}: the samples drawn from bin j (inds == j) are k in [first[j-1], first[j])
     for (int j = lane; j < S; j += 32) {
@@ -287,7 +319,7 @@ extern "C" const char *snf_error_string(int code) {
 }
 
 // hier_kernel needs up to 51 KB of dynamic shared memory at its accepted limits (S = 256, n_new = 512): opt in per device
-constexpr int kHierMaxSmem = 64 * 1024;
+constexpr int kHierMaxSmem = 72 * 1024;
 int snf_sampling_set_attributes() {
   cudaError_t e = cudaSuccess;
 #define SNF_ATTR(PER) \
@@ -297,9 +329,8 @@ int snf_sampling_set_attributes() {
   return (int)e;
 }
 
-extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals,
-                                     const float *t_rand, int64_t N, int S, float distance, float solar_R,
-                                     float *z_vals, float *points, void *stream) {
+static int sample_bins(const float *rays_o, const float *rays_d, const float *t_vals, const float *t_rand, int64_t N, int S,
+                       float distance, float solar_R, float *z_vals, float *points, int spherical, void *stream) {
   if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(rays_o); SNF_CHECK_PTR(rays_d); SNF_CHECK_PTR(t_vals); SNF_CHECK_PTR(z_vals);
   if (N < 0 || S <= 0) return SNF_E_ARG;
@@ -307,16 +338,27 @@ extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, c
   while (rpw > 1 && N / rpw < 148 * 16) rpw >>= 1;
   const unsigned grid = (unsigned)ceil_div64(N, 8 * rpw);
   if (S == 64)
-    stratified_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw);
+    stratified_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw, spherical);
   else
-    stratified_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw);
+    stratified_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, rpw, spherical);
   count_launch();
   return launch_status();
 }
 
-extern "C" int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in,
-                                 int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds,
-                                 float *cdf_out, void *stream) {
+extern "C" int snf_stratified_sample(const float *rays_o, const float *rays_d, const float *t_vals,
+                                     const float *t_rand, int64_t N, int S, float distance, float solar_R,
+                                     float *z_vals, float *points, void *stream) {
+  return sample_bins(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, 0, stream);
+}
+
+extern "C" int snf_spherical_sample(const float *rays_o, const float *rays_d, const float *t_vals,
+                                    const float *t_rand, int64_t N, int S, float distance, float solar_R,
+                                    float *z_vals, float *points, void *stream) {
+  return sample_bins(rays_o, rays_d, t_vals, t_rand, N, S, distance, solar_R, z_vals, points, 1, stream);
+}
+
+static int hier_launch(const float *z_vals, const float *weights, const float *u, const float *cdf_in, int64_t N, int S,
+                       int n_new, float *new_z, float *z_comb, int64_t *inds, float *cdf_out, int u_per_ray, void *stream) {
   if (N == 0) return 0;   // an empty batch is valid (and its tensors have null data pointers)
   SNF_CHECK_PTR(z_vals); SNF_CHECK_PTR(u); SNF_CHECK_PTR(new_z); SNF_CHECK_PTR(z_comb);
   if (weights == nullptr && cdf_in == nullptr) return SNF_E_ARG;
@@ -324,19 +366,31 @@ extern "C" int snf_hier_resample(const float *z_vals, const float *weights, cons
   if (S > 256 || n_new > 512) return SNF_E_SHAPE;
   const int warps = 4;
   const int ncnt = (S > n_new ? S : n_new) + 2;
-  const size_t smem = ((size_t)n_new + (size_t)warps * (3 * S + n_new + (S + n_new) + 2 * S + ncnt)) * sizeof(float);
+  const size_t smem = ((size_t)n_new + (size_t)warps * (3 * S + n_new + (S + n_new) + 2 * S + ncnt + (u_per_ray ? n_new : 0))) * sizeof(float);
   if (smem > (size_t)kHierMaxSmem) return SNF_E_SHAPE;
   if (smem > 48 * 1024)
     if (int e = snf_device_setup(nullptr)) return e;
   const unsigned grid = (unsigned)ceil_div64(N, warps);
 #define SNF_LAUNCH(PER) \
-  hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out)
+  hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out, u_per_ray)
   const int per = (n_new + 31) / 32;
   if (per <= 1) SNF_LAUNCH(1); else if (per <= 2) SNF_LAUNCH(2); else if (per <= 4) SNF_LAUNCH(4);
   else if (per <= 8) SNF_LAUNCH(8); else SNF_LAUNCH(16);
 #undef SNF_LAUNCH
   count_launch();
   return launch_status();
+}
+
+extern "C" int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in,
+                                 int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds,
+                                 float *cdf_out, void *stream) {
+  return hier_launch(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out, 0, stream);
+}
+
+extern "C" int snf_hier_resample_perturb(const float *z_vals, const float *weights, const float *u_rand, const float *cdf_in,
+                                         int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds,
+                                         float *cdf_out, void *stream) {
+  return hier_launch(z_vals, weights, u_rand, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out, 1, stream);
 }
 
 extern "C" int snf_make_query(const float *rays_o, const float *rays_d, const float *z, const float *times,

@@ -48,6 +48,9 @@ class FusedRender:
         d.n_hidden, d.d_filter = len(self.w_c) - 1, self.w_c[0].shape[0]
         d.out_offset0, d.out_offset1 = [float(v) for v in cm._out_offsets()]
         s = rendering.sampler
+        if getattr(s, '_kind', 'stratified') != 'stratified' or rendering.sampler_hierarchical.perturb:
+            raise SnfError('the one-call C entry renders the default sampler pair (stratified + unperturbed hierarchical); '
+                           'SphericalSampler / HierarchicalSampler(perturb=True) run through the staged classes')
         self.t_vals = s.t_vals.reshape(-1).contiguous()
         self.u = rendering.sampler_hierarchical.u(dev)
         d.t_vals, d.u, d.S, d.n_new = self.t_vals.data_ptr(), self.u.data_ptr(), self.t_vals.numel(), self.u.numel()

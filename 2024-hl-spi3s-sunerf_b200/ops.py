@@ -36,8 +36,10 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
 
 
 # ------------------------------------------------------------------------------------------ sampling
-def stratified_sample(rays_o, rays_d, t_vals, t_rand, distance: float, solar_R: float, want_points: bool = False):
-    """a1 - StratifiedSampler.forward (sunerf/train/sampling.py:68-102). Returns (z_vals[N,S], points or None)."""
+def stratified_sample(rays_o, rays_d, t_vals, t_rand, distance: float, solar_R: float, want_points: bool = False,
+                      spherical: bool = False):
+    """a1 - StratifiedSampler.forward (sunerf/train/sampling.py:68-102), or SphericalSampler.forward (:16-54) with
+    spherical=True.  Returns (z_vals[N,S], points or None)."""
     rays_o, rays_d = _f32(rays_o, 'rays_o'), _f32(rays_d, 'rays_d')
     t_vals = _f32(t_vals, 't_vals').reshape(-1)
     N, S = rays_o.shape[0], t_vals.numel()
@@ -46,17 +48,21 @@ def stratified_sample(rays_o, rays_d, t_vals, t_rand, distance: float, solar_R: 
         assert tuple(t_rand.shape) == (N, S)
     z = torch.empty(N, S, device=rays_o.device, dtype=torch.float32)
     pts = torch.empty(N, S, 3, device=rays_o.device, dtype=torch.float32) if want_points else None
-    _lib.check(_lib.lib().snf_stratified_sample(rays_o.data_ptr(), rays_d.data_ptr(), t_vals.data_ptr(), _ptr(t_rand),
-                                                N, S, float(distance), float(solar_R), z.data_ptr(), _ptr(pts),
-                                                _stream()), 'snf_stratified_sample')
+    fn = _lib.lib().snf_spherical_sample if spherical else _lib.lib().snf_stratified_sample
+    _lib.check(fn(rays_o.data_ptr(), rays_d.data_ptr(), t_vals.data_ptr(), _ptr(t_rand), N, S, float(distance), float(solar_R),
+                  z.data_ptr(), _ptr(pts), _stream()), 'snf_spherical_sample' if spherical else 'snf_stratified_sample')
     return z, pts
 
 
-def hier_resample(z_vals, weights, u, cdf_in=None, want_inds: bool = False, want_cdf: bool = False):
-    """a2 - HierarchicalSampler (sampling.py:111-169). Returns (new_z[N,n], z_comb[N,S+n], inds|None, cdf|None)."""
+def hier_resample(z_vals, weights, u, cdf_in=None, want_inds: bool = False, want_cdf: bool = False, per_ray_u: bool = False):
+    """a2 - HierarchicalSampler (sampling.py:111-169). Returns (new_z[N,n], z_comb[N,S+n], inds|None, cdf|None).
+    u: the shared ascending grid linspace(0,1,n) (perturb=False), or with per_ray_u=True the [N,n] torch.rand draws of
+    perturb=True (sampling.py:144-146)."""
     z_vals, u = _f32(z_vals, 'z_vals'), _f32(u, 'u')
     N, S = z_vals.shape
-    n_new = u.numel()
+    n_new = u.shape[-1] if per_ray_u else u.numel()
+    if per_ray_u and tuple(u.shape) != (N, n_new):
+        raise _lib.SnfError(f'per-ray u must be [N, n_new] = [{N}, {n_new}], got {tuple(u.shape)}')
     weights = _f32(weights, 'weights') if weights is not None else None
     cdf_in = _f32(cdf_in, 'cdf_in') if cdf_in is not None else None
     dev = z_vals.device
@@ -64,9 +70,9 @@ def hier_resample(z_vals, weights, u, cdf_in=None, want_inds: bool = False, want
     z_comb = torch.empty(N, S + n_new, device=dev, dtype=torch.float32)
     inds = torch.empty(N, n_new, device=dev, dtype=torch.int64) if want_inds else None
     cdf = torch.empty(N, S - 1, device=dev, dtype=torch.float32) if want_cdf else None
-    _lib.check(_lib.lib().snf_hier_resample(z_vals.data_ptr(), _ptr(weights), u.data_ptr(), _ptr(cdf_in), N, S, n_new,
-                                            new_z.data_ptr(), z_comb.data_ptr(), _ptr(inds), _ptr(cdf), _stream()),
-               'snf_hier_resample')
+    fn = _lib.lib().snf_hier_resample_perturb if per_ray_u else _lib.lib().snf_hier_resample
+    _lib.check(fn(z_vals.data_ptr(), _ptr(weights), u.data_ptr(), _ptr(cdf_in), N, S, n_new, new_z.data_ptr(), z_comb.data_ptr(),
+                  _ptr(inds), _ptr(cdf), _stream()), 'snf_hier_resample')
     return new_z, z_comb, inds, cdf
 
 

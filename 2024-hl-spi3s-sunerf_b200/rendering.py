@@ -17,7 +17,7 @@ from torch import nn
 from . import ops
 from ._lib import SnfError
 from .model import NeRF
-from .sampling import HierarchicalSampler, StratifiedSampler
+from .sampling import HierarchicalSampler, SphericalSampler, StratifiedSampler
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 
@@ -100,7 +100,7 @@ class SuNeRFRendering(nn.Module):
         if sampling_type == 'stratified':
             self.sampler = StratifiedSampler(Rs_per_ds=Rs_per_ds, **sampling_config)
         elif sampling_type == 'spherical':
-            raise NotImplementedError('SphericalSampler is optional in the reference and outside the hot path')
+            self.sampler = SphericalSampler(Rs_per_ds=Rs_per_ds, **sampling_config)
         else:
             raise ValueError(f'Unknown sampling type {sampling_type}')
         hierarchical_sampling_type = hierarchical_sampling_config.pop('type')

@@ -29,20 +29,30 @@ class StratifiedSampler(torch.nn.Module):
             t_rand = torch.rand((rays_o.shape[0], self.t_vals.shape[1]), device=rays_o.device)
         if not self.perturb:
             t_rand = None
-        return ops.stratified_sample(rays_o, rays_d, self.t_vals, t_rand, self._distance, self._solar_R, want_points)
+        return ops.stratified_sample(rays_o, rays_d, self.t_vals, t_rand, self._distance, self._solar_R, want_points,
+                                     spherical=getattr(self, '_kind', 'stratified') == 'spherical')
 
     def forward(self, rays_o: torch.Tensor, rays_d: torch.Tensor):
         z, pts = self.sample_z(rays_o, rays_d, want_points=True)
         return {'points': pts, 'z_vals': z}
 
 
+class SphericalSampler(StratifiedSampler):
+    """sampling.py:4-54: bins between the ray's entry and exit of the sphere of radius `distance` (default 2 R_sun), the far end
+    clipped at the solar surface; rays that miss the sphere get NaN rows, as in the reference.  Same buffers, same jitter
+    draw, same kernel as the stratified sampler with the other pair of bin ends."""
+
+    def __init__(self, Rs_per_ds, distance=2.0, n_samples=64, perturb=True):
+        super().__init__(Rs_per_ds, distance=distance, n_samples=n_samples, perturb=perturb)
+        self._kind = 'spherical'
+
+
 class HierarchicalSampler(torch.nn.Module):
-    """sampling.py:104-169 (perturb=False, the reference default and the only mode its configs use)."""
+    """sampling.py:104-169.  perturb=False (the reference default): u = linspace(0, 1, n).  perturb=True (:144-146): one row
+    of torch.rand draws per ray, drawn here with the reference's call (shape [N, n], the rays' device) or passed as `u`."""
 
     def __init__(self, n_samples=128, perturb=False):
         super().__init__()
-        if perturb:
-            raise NotImplementedError('HierarchicalSampler(perturb=True) is not used by any reference config')
         self.n_samples, self.perturb = n_samples, perturb
         self._u = None
 
@@ -51,8 +61,13 @@ class HierarchicalSampler(torch.nn.Module):
             self._u = torch.linspace(0., 1., self.n_samples).to(device)   # host linspace == the reference's values
         return self._u
 
-    def resample(self, z_vals, weights):
-        new_z, z_comb, _, _ = ops.hier_resample(z_vals, weights.detach(), self.u(z_vals.device))
+    def resample(self, z_vals, weights, u=None):
+        if self.perturb or u is not None:
+            if u is None:
+                u = torch.rand(list(z_vals.shape[:-1]) + [self.n_samples], device=z_vals.device)     # sampling.py:145
+            new_z, z_comb, _, _ = ops.hier_resample(z_vals, weights.detach(), u, per_ray_u=True)
+        else:
+            new_z, z_comb, _, _ = ops.hier_resample(z_vals, weights.detach(), self.u(z_vals.device))
         return new_z, z_comb
 
     def forward(self, rays_o, rays_d, z_vals, weights):

@@ -42,6 +42,13 @@ int snf_stratified_sample(const float *rays_o, const float *rays_d, const float 
                           int64_t N, int S, float distance, float solar_R, float *z_vals, float *points,
                           void *stream);
 
+/* SphericalSampler.forward, sunerf/train/sampling.py:16-54 (selectable through sampling_config {'type': 'spherical'},
+ * base_tracing.py:27-28): bins between the ray's entry and exit of the sphere of radius `distance`, the far end clipped
+ * at the solar surface; NaN rows for rays that miss the sphere, as in the reference.  Same arguments as above. */
+int snf_spherical_sample(const float *rays_o, const float *rays_d, const float *t_vals, const float *t_rand,
+                         int64_t N, int S, float distance, float solar_R, float *z_vals, float *points,
+                         void *stream);
+
 /* ---- a2: HierarchicalSampler.forward + sample_pdf, sampling.py:111-169 (perturb=False) --------------
  * z_vals[N,S], weights[N,S] (coarse weights), u[n_new] = linspace(0,1,n_new).
  * cdf_in[N,S-1]: optional externally supplied CDF (stage-boundary parity test); NULL -> built here.
@@ -49,6 +56,11 @@ int snf_stratified_sample(const float *rays_o, const float *rays_d, const float 
  * searchsorted(right=True) result) and cdf_out[N,S-1].  S<=256, n_new<=512. */
 int snf_hier_resample(const float *z_vals, const float *weights, const float *u, const float *cdf_in, int64_t N,
                       int S, int n_new, float *new_z, float *z_comb, int64_t *inds, float *cdf_out, void *stream);
+/* HierarchicalSampler(perturb=True), sampling.py:144-146: u_rand[N,n_new] is the torch.rand draw of :145 (one row of
+ * unordered uniforms per ray, drawn by the host exactly as the reference does); everything else as above. */
+int snf_hier_resample_perturb(const float *z_vals, const float *weights, const float *u_rand, const float *cdf_in,
+                              int64_t N, int S, int n_new, float *new_z, float *z_comb, int64_t *inds, float *cdf_out,
+                              void *stream);
 
 /* ---- a3: query = cat(o + d*z, t), sunerf/rendering/base_tracing.py:64-65, 83-84; sampling.py:100 ---- */
 /* N1: observer image rays on the device.  Replaces get_rays (sunerf/data/ray_sampling.py:7-36) for the

@@ -71,6 +71,30 @@ def stratified_sample(rays_o: torch.Tensor, rays_d: torch.Tensor, t_vals: torch.
     return {'points': pts, 'z_vals': z}
 
 
+def spherical_sample(rays_o: torch.Tensor, rays_d: torch.Tensor, t_vals: torch.Tensor,
+                     t_rand: Optional[torch.Tensor], distance: torch.Tensor,
+                     solar_R: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """SphericalSampler.forward, sampling.py:16-54 (selected by sampling_config {'type': 'spherical'},
+    base_tracing.py:27-28): bins between the entry and exit of the sphere of radius `distance`
+    (NaN for rays that miss it), far end clipped at the solar surface."""
+    qa = rays_d.pow(2).sum(-1)                                      # :24
+    qb = (2 * rays_o * rays_d).sum(-1)                              # :25
+    qc = rays_o.pow(2).sum(-1) - distance ** 2                      # :26
+    near = (-qb - torch.sqrt(qb.pow(2) - 4 * qa * qc)) / (2 * qa)   # :27
+    far = (-qb + torch.sqrt(qb.pow(2) - 4 * qa * qc)) / (2 * qa)    # :28
+    qc = rays_o.pow(2).sum(-1) - solar_R ** 2                       # :32
+    hit = (-qb - torch.sqrt(qb.pow(2) - 4 * qa * qc)) / (2 * qa)    # :33
+    far = torch.where(torch.isnan(hit), far, hit)                   # :35-36
+    z = near[:, None] * (1. - t_vals) + far[:, None] * t_vals       # :41
+    if t_rand is not None:                                          # :44-49
+        mid = .5 * (z[:, 1:] + z[:, :-1])
+        hi = torch.cat([mid, z[:, -1:]], dim=1)
+        lo = torch.cat([z[:, :1], mid], dim=1)
+        z = lo + (hi - lo) * t_rand
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]   # :51
+    return {'points': pts, 'z_vals': z}
+
+
 # --------------------------------------------------------------------------------------
 # a2  HierarchicalSampler.forward + sample_pdf      sunerf/train/sampling.py:111-169
 # --------------------------------------------------------------------------------------
@@ -109,11 +133,13 @@ def invert_cdf(bins: torch.Tensor, cdf: torch.Tensor, u: torch.Tensor) -> Tuple[
 
 
 def hier_resample(rays_o, rays_d, z_vals, weights, n_new: int = 128,
-                  cdf_override: Optional[torch.Tensor] = None, exact_sum: bool = False) -> Dict[str, torch.Tensor]:
-    """sampling.py:111-126 with perturb=False (:141-143): u = linspace(0,1,n_new)."""
+                  cdf_override: Optional[torch.Tensor] = None, exact_sum: bool = False,
+                  u_rand: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """sampling.py:111-126.  perturb=False (:141-143): u = linspace(0,1,n_new); perturb=True (:144-146):
+    `u_rand[N,n_new]` is the torch.rand draw of :145 passed in explicitly."""
     bins = .5 * (z_vals[..., 1:] + z_vals[..., :-1])                 # :118
     cdf = pdf_to_cdf(weights[..., 1:-1], exact_sum) if cdf_override is None else cdf_override
-    u = torch.linspace(0., 1., n_new)
+    u = torch.linspace(0., 1., n_new) if u_rand is None else u_rand
     new_z, inds = invert_cdf(bins, cdf, u)
     new_z = new_z.detach()                                           # :120
     z_comb, _ = torch.sort(torch.cat([z_vals, new_z], dim=-1), dim=-1)  # :123

@@ -148,3 +148,18 @@ def test_adam_step_matches_torch():
     assert gn > 0.5 and all(not torch.equal(a, b) for a, b in zip(before, p))
     # first Adam step moves every coordinate by ~lr regardless of scale
     assert abs((before[0] - p[0].detach()).abs().max().item() - 1e-4) < 1e-6
+
+
+def test_optional_samplers_match_reference_golden():
+    """SphericalSampler (sampling.py:4-54) and HierarchicalSampler(perturb=True) (:144-146): the oracle restatements
+    against vectors produced by the reference's own classes (oracle/make_golden_samplers.py)."""
+    g = golden('samplers_optional.npz')
+    tt = lambda k: torch.from_numpy(g[k])
+    same = lambda a, b: bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+    out = orc.spherical_sample(tt('sph.rays_o'), tt('sph.rays_d'), tt('sph.t_vals'), tt('sph.t_rand'), tt('sph.distance'), tt('sph.solar_R'))
+    assert same(out['z_vals'], tt('sph.z_vals')) and same(out['points'], tt('sph.points'))
+    out = orc.spherical_sample(tt('sph.rays_o'), tt('sph.rays_d'), tt('sph.t_vals'), None, tt('sph.distance'), tt('sph.solar_R'))
+    assert same(out['z_vals'], tt('sph.z_vals_noperturb'))
+    h = orc.hier_resample(tt('hp.rays_o'), tt('hp.rays_d'), tt('hp.z_vals'), tt('hp.weights'), 128, u_rand=tt('hp.u'))
+    assert same(h['new_z_samples'], tt('hp.new_z')) and same(h['z_vals'], tt('hp.z_comb')) and same(h['cdf'], tt('hp.cdf'))
+    assert bool((h['inds'] == tt('hp.inds')).all())
