@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(_PKG, 'lib')
 # SNF_LIB_NAME: developer-only, lets experiment builds (SNF_NVCC_EXTRA) live next to the product library
 LIB_PATH = os.path.join(LIB_DIR, os.environ.get('SNF_LIB_NAME', 'libsunerf_b200.so'))
 SOURCES = ['snf_sampling.cu', 'snf_rays.cu', 'snf_composite.cu', 'snf_mlp_f32.cu', 'snf_mlp_bf16.cu', 'snf_mlp_bf16_bwd.cu',
-           'snf_optim.cu', 'snf_render.cu']
+           'snf_optim.cu', 'snf_render.cu', 'snf_mlp_x3.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -85,6 +85,8 @@ _PROTOS = {
     'snf_mlp_pack_bf16': (_I, [_P, _P, _P, _P]),
     'snf_mlp_fwd_bf16': (_I, [_P, _L, _P, _F, _F, _P, _P, _I, _P]),
     'snf_mlp_bwd_bf16': (_I, [_P, _L, _P, _P, _P, _P, _P, _P]),
+    'snf_mlp_fwd_x3': (_I, [_P, _L, _P, _F, _F, _P, _P, _I, _P]),
+    'snf_mlp_bwd_x3': (_I, [_P, _L, _P, _P, _P, _P, _P, _P]),
     'snf_simple_star_fwd': (_I, [_P, _L, _F, _F, _F, _F, _F, _P, _P]),
     'snf_composite_emission_fwd': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     'snf_composite_emission_bwd': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),

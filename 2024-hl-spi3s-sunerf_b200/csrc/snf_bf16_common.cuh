@@ -41,14 +41,18 @@ constexpr int BIAS_BYTES = D * 4;
 
 constexpr int FWD_BLOCKS = 2 * 2 + 7 * 16;   // forward weight blocks: layer 0 (2 n-halves x 2 k-slabs) + 7 x (2 x 8)
 constexpr int WT_BLOCKS = 7 * 16;            // W^T blocks for the dgrad chain (layers 1..7)
-// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB]
+// packed buffer: [FWD_BLOCKS x 32 KB][bias 8x512 f32][W_out 2x512 f32][b_out 2 f32 + pad] | [WT_BLOCKS x 32 KB] |
+//                [FWD_BLOCKS x 32 KB: fp16(W - fp16(W)), the low halves for the split-precision forward] |
+//                [WT_BLOCKS x 32 KB: low halves of the W^T blocks for the split-precision dgrad chain]
 constexpr int64_t PACK_W_BYTES = (int64_t)FWD_BLOCKS * WBLK_BYTES;
 constexpr int64_t PACK_BIAS_OFF = PACK_W_BYTES;
 constexpr int64_t PACK_WOUT_OFF = PACK_BIAS_OFF + NH * D * 4;
 constexpr int64_t PACK_BOUT_OFF = PACK_WOUT_OFF + 2 * D * 4;
 constexpr int WOUT_BYTES = 2 * D * 4;        // 4 KB, rides through the weight ring as a pseudo-block
 constexpr int64_t PACK_WT_OFF = (PACK_BOUT_OFF + 16 + 1023) / 1024 * 1024;
-constexpr int64_t PACK_TOTAL_BYTES = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+constexpr int64_t PACK_LO_OFF = PACK_WT_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
+constexpr int64_t PACK_WTLO_OFF = PACK_LO_OFF + (int64_t)FWD_BLOCKS * WBLK_BYTES;
+constexpr int64_t PACK_TOTAL_BYTES = PACK_WTLO_OFF + (int64_t)WT_BLOCKS * WBLK_BYTES;
 
 constexpr int FMT = FMT_F16;                 // operand format of every MMA of the field network
 
@@ -142,9 +146,14 @@ static_assert(8 * (2 * NSTAGE + 18) <= 512, "barrier block");
 struct Bf16Ws {
   uint8_t *enc, *h, *pre, *d;
   GradScale *scale;
+  // split-precision ("x3") forward only: low halves of the encoder image and of the running activations (ping-pong),
+  // high halves as ping-pong when nothing is saved (inference), per-(point, N-half, column group) partial outputs
+  uint8_t *enc_lo, *h_lo[2], *h_pp[2];
+  float2 *part;
   int64_t bytes;
 };
-inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
+// x3: 0 = the fused 16-bit kernels' workspace; 1 = plus what the per-layer split-precision forward needs
+inline Bf16Ws bf16_layout(void *base, int64_t M, int train, int x3 = 0) {
   Bf16Ws w{};
   int64_t tiles = (M + TILE_M - 1) / TILE_M;
   tiles = (tiles + 1) / 2 * 2;
@@ -156,6 +165,14 @@ inline Bf16Ws bf16_layout(void *base, int64_t M, int train) {
     w.pre = p + off; off += tiles * NH * (int64_t)C_BYTES;   // quantised cos(pre), see C_BYTES
     w.d = p + off; off += tiles * NH * (int64_t)A_BYTES;
     w.scale = reinterpret_cast<GradScale *>(p + off); off += 256;
+  }
+  if (x3) {
+    if (!train) { w.enc = p + off; off += tiles * 2 * SLAB_BYTES; }
+    w.enc_lo = p + off; off += tiles * 2 * SLAB_BYTES;
+    for (int i = 0; i < 2; ++i) { w.h_lo[i] = p + off; off += tiles * (int64_t)A_BYTES; }
+    if (!train)
+      for (int i = 0; i < 2; ++i) { w.h_pp[i] = p + off; off += tiles * (int64_t)A_BYTES; }
+    w.part = reinterpret_cast<float2 *>(p + off); off += tiles * TILE_M * 4 * (int64_t)sizeof(float2);
   }
   w.bytes = off > 0 ? off : 256;
   return w;

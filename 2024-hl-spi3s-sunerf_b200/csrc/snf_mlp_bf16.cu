@@ -34,7 +34,8 @@ namespace bf {
 // (layer, n-half, k-slab); CTA r of a pair streams rows [128r, 128r+128) of every block
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, const float *w1, const float *w2,
                                                            const float *w3, const float *w4, const float *w5,
-                                                           const float *w6, const float *w7, uint4 *__restrict__ dst) {
+                                                           const float *w6, const float *w7, uint4 *__restrict__ dst,
+                                                           uint4 *__restrict__ dst_lo) {
   const float *W[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)FWD_BLOCKS * (WBLK_BYTES / 16)) return;
@@ -67,6 +68,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *w0, cons
   o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
   // (r>>3)*1024 + (r&7)*128 + pos*16 == r*128 + pos*16: the image is row-linear, only the chunk order is permuted
   dst[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
+  // low halves fp16(W - fp16(W)) for the split-precision forward (snf_mlp_x3.cu)
+  float lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
+  o.x = pack_f16x2(lo[0], lo[1]); o.y = pack_f16x2(lo[2], lo[3]);
+  o.z = pack_f16x2(lo[4], lo[5]); o.w = pack_f16x2(lo[6], lo[7]);
+  dst_lo[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
 }
 
 __global__ void __launch_bounds__(256) pack_small_kernel(const float *b0, const float *b1, const float *b2,
@@ -510,9 +518,9 @@ using namespace snf;
 // snf_mlp_bf16_bwd.cu
 int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st);
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
-                      float *const *gB, int num_sms, cudaStream_t st);
+                      float *const *gB, int num_sms, int wsplit, cudaStream_t st);
 
-int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train) { return bf::bf16_layout(nullptr, M, train).bytes; }
+int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train, int x3) { return bf::bf16_layout(nullptr, M, train, x3).bytes; }
 
 #ifdef SNF_PROF
 // debug build only: per-CTA cycle counters of the last forward launches ([0] inference, [1] training)
@@ -533,8 +541,9 @@ extern "C" int snf_mlp_pack_bf16(const float *const *W, const float *const *B, v
   for (int l = 0; l <= bf::NH; ++l) { SNF_CHECK_PTR(W[l]); SNF_CHECK_PTR(B[l]); }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t chunks = (int64_t)bf::FWD_BLOCKS * (bf::WBLK_BYTES / 16);
-  bf::pack_weights_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7],
-                                                                          reinterpret_cast<uint4 *>(packed));
+  bf::pack_weights_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(
+      W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7], reinterpret_cast<uint4 *>(packed),
+      reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_LO_OFF));
   const int nsmall = bf::NH * bf::D + 2 * bf::D + 2;
   bf::pack_small_kernel<<<(nsmall + 255) / 256, 256, 0, st>>>(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], W[8], B[8],
                                                              reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_BIAS_OFF));
@@ -563,12 +572,14 @@ int snf_device_setup(int *num_sms_out) {
 
 int snf_bf16_set_attributes_bwd();   // snf_mlp_bf16_bwd.cu
 int snf_sampling_set_attributes();   // snf_sampling.cu
+int snf_x3_set_attributes();         // snf_mlp_x3.cu
 int snf_set_kernel_attributes() {
   cudaError_t e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(bf::mlp_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   if (int r = snf_bf16_set_attributes_bwd()) return r;
+  if (int r = snf_x3_set_attributes()) return r;
   return snf_sampling_set_attributes();
 }
 
@@ -601,9 +612,24 @@ extern "C" int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, f
   return launch_status();
 }
 
+static int mlp_bwd_16(int64_t M, const void *packed, const float *grad_out, void *ws, float *const *gW, float *const *gB,
+                      int wsplit, void *stream);
+
 extern "C" int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
                                 float *const *gW, float *const *gB, void *stream) {
   (void)x;
+  return mlp_bwd_16(M, packed, grad_out, ws, gW, gB, 1, stream);
+}
+
+// backward of snf_mlp_fwd_x3: the 16-bit kernels on the saved high halves, the dgrad chain's W^T operand as (hi, lo)
+extern "C" int snf_mlp_bwd_x3(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
+                              float *const *gW, float *const *gB, void *stream) {
+  (void)x;
+  return mlp_bwd_16(M, packed, grad_out, ws, gW, gB, 2, stream);
+}
+
+static int mlp_bwd_16(int64_t M, const void *packed, const float *grad_out, void *ws, float *const *gW, float *const *gB,
+                      int wsplit, void *stream) {
   SNF_CHECK_PTR(packed); SNF_CHECK_PTR(grad_out); SNF_CHECK_PTR(ws); SNF_CHECK_PTR(gW); SNF_CHECK_PTR(gB);
   SNF_CHECK_ALIGN(grad_out, 8); SNF_CHECK_ALIGN(ws, 1024); SNF_CHECK_ALIGN(packed, 1024);
   if (M <= 0) return SNF_E_ARG;
@@ -611,5 +637,5 @@ extern "C" int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, c
   bf::Bf16Ws w = bf::bf16_layout(ws, M, 1);
   int nsm = 0;
   if (int e = snf_device_setup(&nsm)) return e;
-  return snf_bf16_backward(grad_out, M, packed, w, gW, gB, nsm, (cudaStream_t)stream);
+  return snf_bf16_backward(grad_out, M, packed, w, gW, gB, nsm, wsplit, (cudaStream_t)stream);
 }

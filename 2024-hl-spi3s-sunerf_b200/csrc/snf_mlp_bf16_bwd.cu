@@ -26,7 +26,7 @@ constexpr int WG_THREADS = 192;   // wgrad: producer warp, MMA warp, 4 bias/flus
 // block (l, nh, ks): rows = input feature i (256 per block), k = output feature o (64 per block): B[i][o] = W_l[o][i]
 __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const float *w2, const float *w3, const float *w4,
                                                       const float *w5, const float *w6, const float *w7,
-                                                      uint4 *__restrict__ dst) {
+                                                      uint4 *__restrict__ dst, uint4 *__restrict__ dst_lo) {
   const float *W[7] = {w1, w2, w3, w4, w5, w6, w7};
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)WT_BLOCKS * (WBLK_BYTES / 16)) return;
@@ -40,6 +40,11 @@ __global__ void __launch_bounds__(256) pack_wt_kernel(const float *w1, const flo
   uint4 o;
   o.x = pack_f16x2(v[0], v[1]); o.y = pack_f16x2(v[2], v[3]); o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
   dst[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
+  float lo[8];                                  // low halves: the split-precision dgrad chain (WSPLIT = 2)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = v[j] - __half2float(__float2half_rn(v[j]));
+  o.x = pack_f16x2(lo[0], lo[1]); o.y = pack_f16x2(lo[2], lo[3]); o.z = pack_f16x2(lo[4], lo[5]); o.w = pack_f16x2(lo[6], lo[7]);
+  dst_lo[(int64_t)blk * (WBLK_BYTES / 16) + within] = o;
 }
 
 // ------------------------------------------------------------------------------------------ dgrad chain
@@ -73,6 +78,9 @@ __device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
 // Same overlapped structure as the forward (snf_mlp_bf16.cu): per layer two temporal N-halves, the epilogue of half 0
 // runs under the MMAs of half 1 and keeps its result in registers until the A image may be overwritten; the next
 // layer's MMAs start slab by slab.  Shared-memory layout and barriers: namespace fw (the bias area is unused).
+// WSPLIT = 2 (backward of the split-precision mode): W^T enters as the pair (hi, lo) - the same layer is accumulated over
+// sixteen weight blocks instead of eight, the second eight against the low halves and the same A slabs.
+template <int WSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgrad_bf16_kernel(const DgradParams p) {
   constexpr int NSTAGE = fw::NSTAGE, OFF_RING = fw::OFF_RING, OFF_WOUT = fw::OFF_WOUT, OFF_BAR = fw::OFF_BAR;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -100,7 +108,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + fw::TMEM_SLOT_OFF);
-  const uint8_t *wt = p.packed + PACK_WT_OFF;
+  const uint8_t *wt = p.packed + PACK_WT_OFF, *wt_lo = p.packed + PACK_WTLO_OFF;
+  constexpr int NB = 16 * WSPLIT;               // weight blocks per layer: (part, N-half, k-slab), the N-half outermost
 
   if (warp < EPI_WARP0) {
   reg_dealloc<REGS_CTRL>();
@@ -122,14 +131,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
         const int tile = tp * 2 + (int)rank, next_tile = tile + 2 * npairs;
         for (int l = NH - 1; l >= 1; --l)
-          for (int b = 0; b < 16; ++b) {
+          for (int bb = 0; bb < NB; ++bb) {
+            // consumption order: N-half h, then part (hi, lo), then k-slab
+            const int h = bb / (8 * WSPLIT), part = (bb / 8) % WSPLIT, ks = bb & 7;
+            const int b = h * 8 + ks;                                        // block index inside the layer's 16 blocks
             mbar_wait(bar.empty(s), ph ^ 1);
             mbar_arrive_expect_tx(bar.full(s), WHALF_BYTES);
-            bulk_g2s_hint(sW + s * WHALF_BYTES, wt + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES, WHALF_BYTES, bar.full(s), keep);
-            if (l >= 2) {
-              if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * (C_BYTES / 8), C_BYTES / 8);
-            } else if (next_tile < p.num_tiles) {   // l == 1: the next tile's first two images
-              prefetch_l2(pre_img(next_tile, b < 8 ? NH - 1 : NH - 2) + (b & 7) * (C_BYTES / 8), C_BYTES / 8);
+            bulk_g2s_hint(sW + s * WHALF_BYTES, (part ? wt_lo : wt) + (int64_t)((l - 1) * 16 + b) * WBLK_BYTES + rank * WHALF_BYTES,
+                          WHALF_BYTES, bar.full(s), keep);
+            if (part == 0) {
+              if (l >= 2) {
+                if ((b & 1) == 0) prefetch_l2(pre_img(tile, l - 2) + (b >> 1) * (C_BYTES / 8), C_BYTES / 8);
+              } else if (next_tile < p.num_tiles) {   // l == 1: the next tile's first two images
+                prefetch_l2(pre_img(next_tile, b < 8 ? NH - 1 : NH - 2) + (b & 7) * (C_BYTES / 8), C_BYTES / 8);
+              }
             }
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
@@ -146,8 +161,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
         for (int l = NH - 1; l >= 1; --l) {
           for (int h = 0; h < 2; ++h) {
-            for (int ks = 0; ks < 8; ++ks) {
-              if (h == 0) {
+            for (int kk = 0; kk < 8 * WSPLIT; ++kk) {
+              const int ks = kk & 7;                    // A slab; kk >= 8: the same slabs against the low halves of W^T
+              if (h == 0 && kk < 8) {
                 if (ks == 0) wait_ready(0);
                 else if (ks >= 4) wait_ready(ks - 3);
               }
@@ -156,10 +172,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
               if (elect_one()) {
                 const uint64_t ad = adesc0 + (uint64_t)((ks * SLAB_BYTES) >> 4), bd = bdesc0 + (uint64_t)((s * WHALF_BYTES) >> 4);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (ks | k4) != 0);
+                for (int k4 = 0; k4 < 4; ++k4) mma_ss_2cta(tmem + h * NCHUNK, ad + 2 * k4, bd + 2 * k4, idesc, (kk | k4) != 0);
                 mma_commit_2cta(bar.empty(s), 3);
-                if (ks == 7) mma_commit_2cta(bar.acc(h), 3);
-                if (h == 1 && ks == 3) mma_commit_2cta(bar.acc1a(), 3);   // slabs 0..3 of A are no longer read
+                if (kk == 8 * WSPLIT - 1) mma_commit_2cta(bar.acc(h), 3);
+                if (h == 1 && kk == 8 * (WSPLIT - 1) + 3) mma_commit_2cta(bar.acc1a(), 3);   // slabs 0..3 of A are no longer read
               }
               __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -169,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       }
     } else if (lane == 0) {
       for (int tp = pair; tp * 2 < p.num_tiles; tp += npairs) {
-        for (int blk = 0; blk < WT_BLOCKS; ++blk) {
+        for (int blk = 0; blk < WT_BLOCKS * WSPLIT; ++blk) {
           mbar_wait(bar.full(s), ph);
           mbar_arrive_remote_relaxed(mapa_shared(bar.full(s), 0));   // the data is TMA-written and tensor-core-read
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -625,7 +641,8 @@ using namespace snf;
 int snf_bf16_pack_wt(const float *const *W, void *packed, cudaStream_t st) {
   const int64_t chunks = (int64_t)bf::WT_BLOCKS * (bf::WBLK_BYTES / 16);
   bf::pack_wt_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(
-      W[1], W[2], W[3], W[4], W[5], W[6], W[7], reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_WT_OFF));
+      W[1], W[2], W[3], W[4], W[5], W[6], W[7], reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_WT_OFF),
+      reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(packed) + bf::PACK_WTLO_OFF));
   count_launch();
   return launch_status();
 }
@@ -672,14 +689,16 @@ static int debug_sync(const char *what, cudaStream_t st) {
 }
 
 int snf_bf16_set_attributes_bwd() {
-  cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(bf::mlp_dgrad_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::fw::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(bf::mlp_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::WG_SMEM_BYTES);
   return (int)e;
 }
 
 int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, const bf::Bf16Ws &w, float *const *gW,
-                      float *const *gB, int num_sms, cudaStream_t st) {
+                      float *const *gB, int num_sms, int wsplit, cudaStream_t st) {
   int num_tiles = (int)((M + bf::TILE_M - 1) / bf::TILE_M);
   num_tiles = (num_tiles + 1) / 2 * 2;   // CTA pairs; the workspace is sized for the padding tile
   // gradients are accumulated with atomics: clear them first (ABI: overwritten).  The trainer hands views of one flat
@@ -712,7 +731,8 @@ int snf_bf16_backward(const float *grad_out, int64_t M, const void *packed, cons
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   grid &= ~1;
   BWD_EV(0);
-  bf::mlp_dgrad_bf16_kernel<<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, st>>>(dp);
+  if (wsplit == 2) bf::mlp_dgrad_bf16_kernel<2><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, st>>>(dp);
+  else bf::mlp_dgrad_bf16_kernel<1><<<grid, bf::NTHREADS, bf::fw::SMEM_BYTES, st>>>(dp);
   BWD_EV(1);
   if (int e = debug_sync("mlp_dgrad_bf16_kernel", st)) return e;
 

@@ -283,12 +283,12 @@ inline F32Ws f32_layout(void *base, int64_t M, int n_hidden, int d, int train) {
 using namespace snf;
 
 extern "C" int64_t snf_mlp_pack_bytes(void);
-int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train);   // snf_mlp_bf16.cu
+int64_t snf_mlp_bf16_ws_bytes(int64_t M, int train, int x3);   // snf_mlp_bf16.cu
 
 extern "C" int64_t snf_mlp_ws_bytes(int64_t M, int n_hidden, int d_filter, int mode, int train) {
   if (M < 0 || n_hidden <= 0 || n_hidden > 16 || d_filter <= 0) return SNF_E_ARG;
   if (M == 0) return 256;
-  if (mode == 1) return snf_mlp_bf16_ws_bytes(M, train);
+  if (mode == 1 || mode == 2) return snf_mlp_bf16_ws_bytes(M, train, mode == 2);
   return f32_layout(nullptr, M, n_hidden, d_filter, train).bytes;
 }
 

@@ -51,7 +51,7 @@ int64_t render_layout(const snf_render_desc *d, int64_t N, int train, void *base
 int check_desc(const snf_render_desc *d) {
   SNF_CHECK_PTR(d);
   if (d->kind != 0 && d->kind != 1) return SNF_E_ARG;
-  if (d->mode != 0 && d->mode != 1) return SNF_E_ARG;
+  if (d->mode < 0 || d->mode > 2) return SNF_E_ARG;
   if (d->S < 3 || d->n_new <= 0 || d->S > 256 || d->S + d->n_new > 256) return SNF_E_SHAPE;
   SNF_CHECK_PTR(d->t_vals); SNF_CHECK_PTR(d->u);
   if (d->mode == 0) { SNF_CHECK_PTR(d->W_coarse); SNF_CHECK_PTR(d->B_coarse); SNF_CHECK_PTR(d->W_fine); SNF_CHECK_PTR(d->B_fine); }
@@ -67,6 +67,8 @@ int check_desc(const snf_render_desc *d) {
 int field_fwd(const snf_render_desc *d, bool fine, const float *query, int64_t M, float *raw, void *ws, int train, void *st) {
   if (d->mode == 1)
     return snf_mlp_fwd_bf16(query, M, fine ? d->packed_fine : d->packed_coarse, d->out_offset0, d->out_offset1, raw, ws, train, st);
+  if (d->mode == 2)
+    return snf_mlp_fwd_x3(query, M, fine ? d->packed_fine : d->packed_coarse, d->out_offset0, d->out_offset1, raw, ws, train, st);
   return snf_mlp_fwd_f32(query, M, fine ? d->W_fine : d->W_coarse, fine ? d->B_fine : d->B_coarse, d->n_hidden, d->d_filter,
                          d->out_offset0, d->out_offset1, raw, ws, train, st);
 }
@@ -166,6 +168,9 @@ extern "C" int snf_render_fused_bwd(const snf_render_desc *d, const float *rays_
     if (d->mode == 1)
       SNF_TRY(snf_mlp_bwd_bf16(query, N * s, fine ? d->packed_fine : d->packed_coarse, g_raw, mws, fine ? gW_fine : gW_coarse,
                                fine ? gB_fine : gB_coarse, stream));
+    else if (d->mode == 2)
+      SNF_TRY(snf_mlp_bwd_x3(query, N * s, fine ? d->packed_fine : d->packed_coarse, g_raw, mws, fine ? gW_fine : gW_coarse,
+                             fine ? gB_fine : gB_coarse, stream));
     else
       SNF_TRY(snf_mlp_bwd_f32(query, N * s, fine ? d->W_fine : d->W_coarse, d->n_hidden, d->d_filter, g_raw, mws,
                               fine ? gW_fine : gW_coarse, fine ? gB_fine : gB_coarse, stream));

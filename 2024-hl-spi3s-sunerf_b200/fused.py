@@ -40,7 +40,7 @@ class FusedRender:
         cm, fm = rendering.coarse_model, rendering.fine_model
         if cm.precision != fm.precision:
             raise SnfError('coarse and fine model must use the same precision mode')
-        self.mode = 1 if cm.precision == 'bf16' else 0
+        self.mode = ops.MLP_MODES[cm.precision]
         d = _lib.RenderDesc()
         d.kind, d.mode = (1 if self.dt else 0), self.mode
         ps_c, ps_f = cm.linear_params(), fm.linear_params()
@@ -67,7 +67,7 @@ class FusedRender:
         # host arrays of device pointers (the parameters may have been re-homed, e.g. into RayTrainer's flat buffer)
         self._arrs = [_ptr_array([p.detach() for p in ps]) for ps in (self.w_c, self.b_c, self.w_f, self.b_f)]
         d.W_coarse, d.B_coarse, d.W_fine, d.B_fine = [ctypes.cast(a, ctypes.c_void_p) for a in self._arrs]
-        if self.mode == 1:
+        if self.mode >= 1:
             d.packed_coarse = r.coarse_model._packed_ptr(self.w_c, self.b_c)
             d.packed_fine = r.fine_model._packed_ptr(self.w_f, self.b_f)
         if self.dt:

@@ -96,7 +96,7 @@ class ObserverRenderer:
             ins['t_rand'] = t_rand
         key = tuple((k, tuple(v.shape)) for k, v in ins.items())
         for m in (self.rendering.coarse_model, self.rendering.fine_model):
-            if getattr(m, 'precision', None) == 'bf16':
+            if getattr(m, 'precision', None) in ops.TC_MODES:
                 ps = m.linear_params()
                 m._packed_ptr(ps[0::2], ps[1::2])
         if key != self._g_key:

@@ -5,9 +5,13 @@ state_dict keys kept: in_layer.0.freq_bands, in_layer.1.{w
 out_layer.{weight,bias}, log_absortpion.{94,...,335}, volumetric_constant.  Modules are constructed in the
 reference's order, so `torch.manual_seed(s)` gives bit-identical initial weights.
 
-Extra (non-reference) knob: `precision` = 'fp32' (FFMA SIMT, the 1e-5 parity mode) or 'bf16' (tcgen05 tensor
-cores, the task's "bf16-MLP mode": 1e-2 on intensities, 1e-3 on gradients; its MMA operands are fp16 since round 2,
-'f16' / 'fp16' are accepted as aliases); default from $SUNERF_B200_PRECISION, else 'fp32'.
+Extra (non-reference) knob: `precision` =
+  'fp32'  FFMA SIMT kernels: the 1e-5 parity mode for ANY network shape;
+  'x3'    (alias 'fp32_tc') the same 1e-5 / 1e-3 gates on tcgen05 tensor cores for the default 8 x 512 network: every operand
+          a (hi, lo) fp16 pair, three MMAs per product (csrc/snf_mlp_x3.cu);
+  'bf16'  (aliases 'f16', 'fp16') the task's "bf16-MLP mode" on tcgen05: 1e-2 on intensities, 1e-3 on gradients; its MMA
+          operands are fp16 since round 2.
+Default from $SUNERF_B200_PRECISION, else 'fp32'.
 """
 from __future__ import annotations
 
@@ -25,8 +29,10 @@ def canonical_precision(p: str) -> str:
     p = str(p).lower()
     if p in ('f16', 'fp16', 'tc'):
         p = 'bf16'
-    if p not in ('fp32', 'bf16'):
-        raise ValueError(f'precision must be fp32 or bf16, got {p}')
+    if p in ('fp32_tc', 'fp32x3'):
+        p = 'x3'
+    if p not in ops.MLP_MODES:
+        raise ValueError(f'precision must be one of fp32, x3 (fp32_tc), bf16 - got {p}')
     return p
 
 
@@ -70,7 +76,7 @@ class _FieldMLP(torch.autograd.Function):
     def forward(ctx, x, owner, train, off0, off1, *params):
         weights, biases = list(params[0::2]), list(params[1::2])
         mode = owner.precision
-        packed = owner._packed_ptr(weights, biases) if mode == 'bf16' else None
+        packed = owner._packed_ptr(weights, biases) if mode in ops.TC_MODES else None
         out, ws = ops.mlp_forward(x, weights, biases, (off0, off1), mode=mode, train=train, packed_ptr=packed)
         if train:
             ctx.ws, ctx.packed, ctx.owner = ws, packed, owner

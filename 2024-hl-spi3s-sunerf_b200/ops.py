@@ -13,6 +13,9 @@ import torch
 from . import _lib
 
 AIA_CHANNELS = (94, 131, 171, 193, 211, 304, 335)
+# field-network modes of the C ABI: fp32 SIMT (any shape), 16-bit tensor cores, split-precision tensor cores (8 x 512 only)
+MLP_MODES = {'fp32': 0, 'bf16': 1, 'x3': 2}
+TC_MODES = ('bf16', 'x3')
 
 
 def _stream() -> int:
@@ -115,7 +118,7 @@ class MLPWorkspace:
 
     def __init__(self, M: int, n_hidden: int, d_filter: int, mode: str, train: bool, device):
         self.M, self.n_hidden, self.d_filter, self.mode, self.train = M, n_hidden, d_filter, mode, train
-        nbytes = _lib.lib().snf_mlp_ws_bytes(M, n_hidden, d_filter, 1 if mode == 'bf16' else 0, int(train))
+        nbytes = _lib.lib().snf_mlp_ws_bytes(M, n_hidden, d_filter, MLP_MODES[mode], int(train))
         if nbytes < 0:
             _lib.check(int(nbytes), 'snf_mlp_ws_bytes')
         # 1024-byte aligned base (UMMA/TMA images)
@@ -155,11 +158,12 @@ def mlp_forward(x, weights, biases, out_offsets=(0.0, 0.0), mode: str = 'fp32', 
         bl = [_f32(b, 'b') for b in biases]
         _lib.check(L.snf_mlp_fwd_f32(x.data_ptr(), M, _ptr_array(wl), _ptr_array(bl), n_hidden, d, float(out_offsets[0]),
                                      float(out_offsets[1]), out.data_ptr(), ws.ptr, int(train), _stream()), 'snf_mlp_fwd_f32')
-    elif mode == 'bf16':
+    elif mode in TC_MODES:
         if packed_ptr is None:
-            raise _lib.SnfError('bf16 mode needs packed weights (mlp_pack_bf16)')
-        _lib.check(L.snf_mlp_fwd_bf16(x.data_ptr(), M, packed_ptr, float(out_offsets[0]), float(out_offsets[1]),
-                                      out.data_ptr(), ws.ptr, int(train), _stream()), 'snf_mlp_fwd_bf16')
+            raise _lib.SnfError('the tensor-core modes need packed weights (mlp_pack_bf16)')
+        fn = L.snf_mlp_fwd_bf16 if mode == 'bf16' else L.snf_mlp_fwd_x3
+        _lib.check(fn(x.data_ptr(), M, packed_ptr, float(out_offsets[0]), float(out_offsets[1]), out.data_ptr(), ws.ptr,
+                      int(train), _stream()), 'snf_mlp_fwd_' + mode)
     else:
         raise ValueError(f'unknown MLP mode {mode}')
     return out, ws
@@ -174,8 +178,9 @@ def mlp_backward(x, weights, grad_out, ws: MLPWorkspace, grad_weights, grad_bias
         _lib.check(L.snf_mlp_bwd_f32(x.data_ptr(), ws.M, _ptr_array(wl), ws.n_hidden, ws.d_filter, grad_out.data_ptr(),
                                      ws.ptr, _ptr_array(grad_weights), _ptr_array(grad_biases), _stream()), 'snf_mlp_bwd_f32')
     else:
-        _lib.check(L.snf_mlp_bwd_bf16(x.data_ptr(), ws.M, packed_ptr, grad_out.data_ptr(), ws.ptr,
-                                      _ptr_array(grad_weights), _ptr_array(grad_biases), _stream()), 'snf_mlp_bwd_bf16')
+        fn = L.snf_mlp_bwd_bf16 if ws.mode == 'bf16' else L.snf_mlp_bwd_x3
+        _lib.check(fn(x.data_ptr(), ws.M, packed_ptr, grad_out.data_ptr(), ws.ptr, _ptr_array(grad_weights),
+                      _ptr_array(grad_biases), _stream()), 'snf_mlp_bwd_' + ws.mode)
 
 
 def simple_star(x, rho_0: float, h0: float, T0: float, R_s: float, t_photosphere: float):

@@ -128,7 +128,7 @@ class RayTrainer:
     def _field(self, model, query, train=True):
         ps = model.linear_params()
         weights, biases = ps[0::2], ps[1::2]
-        packed = model._packed_ptr(weights, biases) if model.precision == 'bf16' else None
+        packed = model._packed_ptr(weights, biases) if model.precision in ops.TC_MODES else None
         out, ws = ops.mlp_forward(query.view(-1, 4), weights, biases, model._out_offsets(), mode=model.precision,
                                   train=train, packed_ptr=packed)
         return out, ws, weights, packed

@@ -78,7 +78,7 @@ int snf_make_query(const float *rays_o, const float *rays_d, const float *z, con
  * W, B: HOST arrays of n_hidden+1 device pointers in nn.Linear layout (weight[out,in]).
  * fp32 entry points: FFMA SIMT, the 1e-5 parity mode.  ws: workspace of snf_mlp_ws_bytes() bytes.
  * train!=0 keeps every layer's activation and cosine in ws for snf_mlp_bwd_f32. */
-int64_t snf_mlp_ws_bytes(int64_t M, int n_hidden, int d_filter, int mode /*0 fp32, 1 bf16*/, int train);
+int64_t snf_mlp_ws_bytes(int64_t M, int n_hidden, int d_filter, int mode /*0 fp32 SIMT, 1 16-bit tensor cores, 2 split-precision tensor cores*/, int train);
 int snf_mlp_fwd_f32(const float *x /*[M,4]*/, int64_t M, const float *const *W, const float *const *B,
                     int n_hidden, int d_filter, float out_offset0, float out_offset1, float *out /*[M,2]*/,
                     void *ws, int train, void *stream);
@@ -98,6 +98,16 @@ int snf_mlp_fwd_bf16(const float *x, int64_t M, const void *packed, float out_of
                      float *out, void *ws, int train, void *stream);
 int snf_mlp_bwd_bf16(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
                      float *const *gW, float *const *gB, void *stream);
+
+/* Split-precision tensor-core entry points: the 1e-5 "fp32 mode" of the default 8 x 512 network on tcgen05.  Every
+ * operand of the forward is the pair (fp16(v), fp16(v - fp16(v))) and every product three MMAs into one fp32 accumulator
+ * (csrc/snf_mlp_x3.cu); the backward is the 16-bit one with the W^T operand of the dgrad chain split in two.  Same
+ * `packed` buffer as above (snf_mlp_pack_bf16 also writes the low halves); ws: snf_mlp_ws_bytes(M, 8, 512, 2, train)
+ * bytes, 1024-byte aligned.  Intensities ~3e-7, per-parameter gradients ~1e-4 of the reference's. */
+int snf_mlp_fwd_x3(const float *x, int64_t M, const void *packed, float out_offset0, float out_offset1,
+                   float *out, void *ws, int train, void *stream);
+int snf_mlp_bwd_x3(const float *x, int64_t M, const void *packed, const float *grad_out, void *ws,
+                   float *const *gW, float *const *gB, void *stream);
 
 /* ---- a7: SimpleStar.forward, sunerf/model/stellar_model.py:53-102 --------------------------------- */
 int snf_simple_star_fwd(const float *x /*[M,4]*/, int64_t M, float rho_0, float h0, float T0, float R_s,
@@ -160,7 +170,8 @@ int snf_adam_step_sched(float *params, const float *grads, float *exp_avg, float
  * the W_x / B_x arrays themselves (HOST arrays of n_hidden+1 device pointers, as in snf_mlp_fwd_f32). */
 typedef struct snf_render_desc {
   int kind;                 /* 0: EmissionRadiativeTransfer (emission.py:14-54), 1: DensityTemperatureRadiativeTransfer */
-  int mode;                 /* 0: fp32 field networks (W_x / B_x), 1: bf16 tensor cores (packed_x from snf_mlp_pack_bf16) */
+  int mode;                 /* 0: fp32 SIMT field networks (W_x / B_x); 1: 16-bit tensor cores, 2: split-precision tensor cores
+                             * (both: packed_x from snf_mlp_pack_bf16) */
   int n_hidden, d_filter;   /* 8, 512 */
   const float *const *W_coarse, *const *B_coarse, *const *W_fine, *const *B_fine;
   const void *packed_coarse, *packed_fine;

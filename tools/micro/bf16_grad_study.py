@@ -28,6 +28,9 @@ def rnd(t, kind):
         return bf(t)
     if kind == 'fp16':
         return t.to(torch.float16).float()
+    if kind == 'split16':                   # hi + lo fp16 pair (lo may be subnormal: absolute floor 2^-25)
+        hi = t.to(torch.float16).float()
+        return hi + (t - hi).to(torch.float16).float()
     if kind == 'split':                     # hi + lo bf16 pair: 16 mantissa bits
         hi = bf(t)
         return hi + bf(t - hi)
@@ -63,10 +66,12 @@ class EmuMLP(torch.autograd.Function):
         n = len(ws)
         h = rnd(orc.positional_encoding(x), 'bf16' if cfg['h'] == 'u16phase' else cfg['h'])
         hs, coss = [h], []
+        ctx_full = []
         for i in range(n - 1):
             pre = F.linear(h, rnd(ws[i], cfg['w'])) + bs[i]
             coss.append(cos_of(pre, cfg['cos']))
             h_full = torch.sin(pre)
+            ctx_full.append(h_full)
             if cfg['h'] == 'u16phase':
                 q = torch.round(pre * (65536.0 / (2 * torch.pi)))
                 h = torch.sin(q * (2 * torch.pi / 65536.0))
@@ -74,6 +79,8 @@ class EmuMLP(torch.autograd.Function):
                 h = rnd(h_full, cfg['h'])
             hs.append(h)
         out = F.linear(h_full, ws[-1], bs[-1])          # output layer: fp32 registers on the unrounded h_7
+        if 'h_bwd' in cfg:                      # the backward reads another rounding of the saved activations / weights
+            hs = [rnd(orc.positional_encoding(x), cfg['h_bwd'])] + [rnd(t_, cfg['h_bwd']) for t_ in ctx_full]
         ctx.cfg, ctx.hs, ctx.coss, ctx.ws, ctx.h7 = cfg, hs, coss, ws, h_full
         return out
 
@@ -98,7 +105,7 @@ class EmuMLP(torch.autograd.Function):
             grads[2 * i] = dpre.t() @ hs[i]
             grads[2 * i + 1] = dpre.sum(0)
             if i > 0:
-                dh = dpre @ rnd(ws[i], cfg['w'])
+                dh = dpre @ rnd(ws[i], cfg.get('w_bwd', cfg['w']))
         return (None, None) + tuple(grads)
 
 
@@ -173,14 +180,9 @@ def main():
     img_ref, g_ref = run(None, b)
     base = dict(w='bf16', h='bf16', cos='int8', dpre='bf16')
     f16 = dict(w='fp16', h='fp16', cos='fp16', dpre='bf16')
-    f16 = dict(w='fp16', h='fp16', cos='i8half', dpre='bf16')
-    variants = [('f16, dpre bf16', f16),
-                ('f16, dpre fp16 scaled (kernels)', dict(f16, dpre='fp16s')),
-                ('f16, dpre fp32', dict(f16, dpre='fp32')),
-                ('only w fp16', dict(w='fp16', h='fp32', cos='fp32', dpre='fp32')),
-                ('only h fp16', dict(w='fp32', h='fp16', cos='fp32', dpre='fp32')),
-                ('only dpre fp16 scaled', dict(w='fp32', h='fp32', cos='fp32', dpre='fp16s')),
-                ('all fp32 (emulation floor)', dict(w='fp32', h='fp32', cos='fp32', dpre='fp32')),
+    variants = [('16-bit mode (kernels)', dict(w='fp16', h='fp16', cos='i8half', dpre='fp16s')),
+                ('x3: split fwd + 16-bit bwd', dict(w='split16', h='split16', cos='i8half', dpre='fp16s', w_bwd='fp16', h_bwd='fp16')),
+                ('x3: split fwd + 16-bit bwd, split W^T', dict(w='split16', h='split16', cos='i8half', dpre='fp16s', w_bwd='split16', h_bwd='fp16')),
                 ]
     if os.environ.get('STUDY_ONLY'):
         variants = [v for v in variants if v[0].startswith(tuple(os.environ['STUDY_ONLY'].split(',')))]
