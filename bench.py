@@ -182,7 +182,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('SUNERF_B200_PRECISION', 'bf16'), choices=['fp32', 'x3', 'bf16'])
     ap.add_argument('--ref-rays', type=int, default=RAYS_PER_GPU, help='rays per step of the reference arm (default: the full config batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial-backward', action='store_true', help='coarse backward after the fine one instead of beside it (A/B aid)')
@@ -325,6 +325,37 @@ def main():
     renderer.render_observer_image(0.05, 1.0, 3.0, batch_size=RENDER_BATCH, rows=slice(0, 16), as_numpy=False)   # warm-up
     ms_image = timed_loop(image_once, 1)
 
+    # ---- the exact mode on tensor cores (precision 'x3': fp32-mode gates, three fp16 MMAs per product) on the same workload
+    exact = None
+    if args.precision == 'bf16':
+        torch.manual_seed(7)
+        rx = s.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'precision': 'x3'}).to(dev)
+        tx = s.RayTrainer(rx, use_cuda_graph=not args.no_cuda_graph)
+
+        def step_x3():
+            return tx.step(devb['rays_o'], devb['rays_d'], devb['times'], devb['target'],
+                           t_rand=torch.rand((N, S_COARSE), device=dev, generator=gen))
+        for _ in range(4):
+            step_x3()
+        nx = max(5, args.steps // 2)
+        ms_x = timed_loop(step_x3, nx) / nx
+        tx.check_finite()
+        del tx
+
+        def render_x3():
+            with torch.no_grad():
+                return rx(rdev['rays_o'], rdev['rays_d'], rdev['times'])
+        for _ in range(2):
+            render_x3()
+        ms_rx = timed_loop(render_x3, 5) / 5
+        exact = {'precision': 'x3 (split-precision fp16 pairs on tcgen05; gates 1e-5 intensities / 1e-3 gradients)',
+                 'train_rays_per_s': N * world / (ms_x * 1e-3), 'ms_per_step': ms_x,
+                 'tensor_flop_frac': N * (S_COARSE + S_FINE) * (3 * FLOP_FWD_POINT + 7 * 2 * 512 * 512 * 2 + (84 + 7 * 512) * 512 * 2)
+                 / (ms_x * 1e-3) / 1e12 / pk['tflops'],
+                 'render_Msamples_per_s': RENDER_BATCH * (S_COARSE + S_FINE) * world / (ms_rx * 1e-3) / 1e6, 'ms_per_render_batch': ms_rx}
+        del rx
+        torch.cuda.empty_cache()
+
     # ---- render_mhd.yaml as shipped (BASELINE.json configs[4]): density-temperature head, C = 6, pixel_intensity_factor
     #      1e10 (image_render.py:267), field = SimpleStar (render_mhd.yaml:1) and a trained-size NeRF_DT: a 4096-ray batch
     #      and the 1024^2 image each
@@ -394,7 +425,8 @@ def main():
     step_tflops = N * FLOP_TRAIN_RAY / (ms / args.steps * 1e-3) / 1e12
     line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f16 operands (weights, activations, scaled gradients), f32 accumulate' if args.precision == 'bf16' else 'f32',
+            'vs_baseline': None, 'dtype': {'bf16': 'f16 operands (weights, activations, scaled gradients), f32 accumulate',
+                                           'x3': 'f16 (hi, lo) operand pairs, 3 MMAs per product, f32 accumulate', 'fp32': 'f32'}[args.precision],
             'data': 'synthetic',
             'config': workload_config(world),
             'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
@@ -423,6 +455,7 @@ def main():
                        'image_1024': {'ms': ms_image, 'Msamples_per_s': 1024 * 1024 * (S_COARSE + S_FINE) / (ms_image * 1e-3) / 1e6,
                                       'what': 'ObserverRenderer.render_observer_image, 1024x1024 pixels, rays generated on the '
                                               'device, rows sharded over ranks, no collective'}},
+            'exact_mode': exact,
             'render_mhd': {'workload': 'render_mhd.yaml: density-temperature head, C=6, F=1e10, hierarchical sampling on; per field a '
                                        '4096-ray batch (ms per batch) and ObserverRenderer.render_observer_image at 1024x1024',
                            **mhd},
