@@ -61,7 +61,8 @@ __device__ __forceinline__ float h_lo(uint32_t u) { return __half2float(__ushort
 __device__ __forceinline__ float h_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 
 // cos(pre) travels from the forward to the dgrad chain as ONE byte: bit 7 = (cos < 0), bits 0..6 = q = rint(127 t) with
-// t = sqrt(1 - |cos|); decode |cos| = 1 - (q/127)^2.  The resolution is finest where the cosines pile up - next to +-1,
+// t = sqrt(1 - |cos|) (127.014 code
+// units per t, COSQ_T); decode |cos| = 1 - (q / 127.014)^2.  The resolution is finest where the cosines pile up - next to +-1,
 // i.e. small pre-activations - and 2/254 at the zero crossings.  Round 1 stored rint(127 cos): every cosine above
 // 1 - 1/254 came back as exactly 1, a one-sided error that does not average out over points and cost 3.4e-3 of
 // per-parameter gradient accuracy by itself; this code costs 1.1e-4 (tools/micro/bf16_grad_study.py, 'i8half').
@@ -69,24 +70,36 @@ __device__ __forceinline__ float h_hi(uint32_t u) { return __half2float(__ushort
 // cos < 0 <=> |s2| > |c2|, and sin(pre) = 2 s2 c2 - two MUFU per element as before.
 // Encode: t' + 1.5 * 2^23 leaves the integer in the low mantissa byte.
 constexpr float COSQ_MAGIC = 12582912.f;
-constexpr float COSQ_SCALE = 179.60512f;     // 127 sqrt(2)
+constexpr float COSQ_SCALE = 179.625f;       // code units per min(|s|, |c|): 127 sqrt(2) rounded to an fp16 value (0.011 % above)
+constexpr float COSQ_T = 127.0140556f;       // = COSQ_SCALE / sqrt(2): code units per t = sqrt(1 - |cos|)
+constexpr float COSQ_INV_T2 = 6.1986403e-5f;  // 1 / COSQ_T^2
 __device__ __forceinline__ uint32_t cosq_enc(float s2, float c2) {
   const float as = fabsf(s2), ac = fabsf(c2);
   const uint32_t q = __float_as_uint(fmaf(fminf(as, ac), COSQ_SCALE, COSQ_MAGIC));
   return as > ac ? (q | 0x80u) : q;
 }
+// Two codes at once from fp16 pairs (s, c) = (sin, cos)(pre / 2): byte 0 and byte 2 of the result hold the codes of the low
+// and high element.  min(|s|, |c|) 127 sqrt(2) + 1024 is an fp16 integer 1024 + q (spacing 1 there: the add rounds to
+// nearest), i.e. the halves 0x64qq.
+__device__ __forceinline__ uint32_t cosq_enc2(__half2 s, __half2 c) {
+  const __half2 as = __habs2(s), ac = __habs2(c);
+  const __half2 qh = __hfma2(__hmin2(as, ac), __float2half2_rn(COSQ_SCALE), __float2half2_rn(1024.f));
+  const uint32_t neg = __hgt2_mask(as, ac);                      // 0xFFFF per element with cos(pre) < 0
+  return (*reinterpret_cast<const uint32_t *>(&qh) & 0x00FF00FFu) | (neg & 0x00800080u);
+}
 __device__ __forceinline__ uint32_t cosq_pack4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3) {   // low bytes -> 4 codes
   return __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
 }
-// Decode codes 2 pr, 2 pr + 1 of the word w as a half2 (packed fp16 arithmetic: q <= 127 is exact, q^2 rounds at 2^-11
-// relative, far below the code's own step): halves 0x64qq = 1024 + q.
-template <int PR> __device__ __forceinline__ __half2 cosq_dec2(uint32_t w) {
-  const uint32_t hq = __byte_perm(w & 0x7F7F7F7Fu, 0x64646464u, PR == 0 ? 0x4140 : 0x4342);
-  const __half2 q = __hsub2(*reinterpret_cast<const __half2 *>(&hq), __float2half2_rn(1024.f));
-  const __half2 c = __hfma2(__hmul2(q, q), __float2half2_rn(-1.f / 16129.f), __float2half2_rn(1.f));
-  const uint32_t sg = __byte_perm(w, 0u, PR == 0 ? 0x1404 : 0x3424) & 0x80008000u;   // code bit 7 -> fp16 sign bit
-  const uint32_t cb = *reinterpret_cast<const uint32_t *>(&c) ^ sg;
-  return *reinterpret_cast<const __half2 *>(&cb);
+// Decode code B (0..3) of the word w in fp32: the byte lands in the low mantissa bits of 2^23, the subtraction is exact.
+// (An fp16 decode was measured first: fp16 cannot tell 1 - q^2/T^2 from 1 for q <= 2 and rounds every cosine above 0.9998
+// to exactly 1 - the round-1 pile-up again, 16 times smaller; together with an fp16 x fp16 product it cost 4.5e-4 of
+// per-parameter gradient accuracy, against 1.1e-4 for this form.  tools/micro/bf16_grad_study.py, 'x3 fp16 decode'.)
+template <int B> __device__ __forceinline__ float cosq_dec(uint32_t w) {
+  const uint32_t f = __byte_perm(w & 0x7F7F7F7Fu, 0x4B000000u, 0x7650 + B);
+  const float q = __uint_as_float(f) - 8388608.f;
+  const float c = fmaf(q * q, -COSQ_INV_T2, 1.f);
+  const uint32_t sg = (B == 3 ? w : (w << (24 - 8 * B))) & 0x80000000u;   // code bit 7 -> sign bit
+  return __uint_as_float(__float_as_uint(c) ^ sg);
 }
 
 // One power-of-two scale per backward call keeps the fp16 dL/dpre images in range: S = 2^-ceil(log2(bound)) with

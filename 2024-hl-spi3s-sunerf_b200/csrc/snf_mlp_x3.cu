@@ -113,7 +113,7 @@ __device__ __forceinline__ void sincos_reduced(float v, float &s, float &c) {
 }
 // the backward's one-byte cosine code (snf_bf16_common.cuh) from the cosine itself
 __device__ __forceinline__ uint32_t cosq_enc_full(float c) {
-  const uint32_t q = __float_as_uint(fmaf(sqrtf(1.f - fabsf(c)), 127.f, COSQ_MAGIC));
+  const uint32_t q = __float_as_uint(fmaf(sqrtf(1.f - fabsf(c)), COSQ_T, COSQ_MAGIC));
   return c < 0.f ? (q | 0x80u) : q;
 }
 

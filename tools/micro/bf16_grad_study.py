@@ -50,6 +50,13 @@ def cos_of(pre, kind):
     if kind == 'i8half':                    # 7-bit magnitude of sqrt(1-|c|) (half-angle code) + sign bit
         tq = torch.round(127.0 * torch.sqrt(1 - c.abs())) / 127.0
         return torch.sign(c) * (1 - tq * tq)
+    if kind == 'i8half_k':                  # the kernels' arithmetic: encode with T = 127.014, decode in fp16 pairs
+        T = 127.0140556
+        q = torch.round(T * torch.sqrt(1 - c.abs())).clamp(max=127)
+        h = lambda t_: t_.to(torch.float16).float()
+        q2 = h(q * q)
+        mag = h(q2 * h(torch.tensor(-1.0 / (T * T))) + 1.0)
+        return torch.sign(c) * mag
     if kind == 'i8angle':                   # 8-bit folded phase acos(c) in [0, pi]
         ph = torch.round(torch.acos(c.clamp(-1, 1)) * (255.0 / torch.pi)) * (torch.pi / 255.0)
         return torch.cos(ph)
@@ -93,12 +100,14 @@ class EmuMLP(torch.autograd.Function):
         grads[2 * (n - 1) + 1] = g.sum(0)
         dh = g @ ws[-1]
         S = 1.0
-        if cfg['dpre'] == 'fp16s':              # fp16 with one power-of-two scale per call (GradScale of the kernels)
+        if cfg['dpre'] in ('fp16s', 'fp16s2'):  # fp16 with one power-of-two scale per call (GradScale of the kernels)
             import math
             bound = g.abs().max().item() * (ws[-1][0].abs() + ws[-1][1].abs()).max().item()
             S = 2.0 ** (-math.frexp(bound)[1]) if bound > 0 else 1.0
         for i in range(n - 2, -1, -1):
-            if cfg['dpre'] == 'fp16s':
+            if cfg['dpre'] == 'fp16s2':         # the kernels' double rounding: fp16(fp16(S dh) * cos)
+                dpre = ((dh * S).to(torch.float16).float() * coss[i]).to(torch.float16).float() / S
+            elif cfg['dpre'] == 'fp16s':
                 dpre = (dh * coss[i] * S).to(torch.float16).float() / S
             else:
                 dpre = rnd(dh * coss[i], cfg['dpre'])
@@ -180,9 +189,13 @@ def main():
     img_ref, g_ref = run(None, b)
     base = dict(w='bf16', h='bf16', cos='int8', dpre='bf16')
     f16 = dict(w='fp16', h='fp16', cos='fp16', dpre='bf16')
-    variants = [('16-bit mode (kernels)', dict(w='fp16', h='fp16', cos='i8half', dpre='fp16s')),
-                ('x3: split fwd + 16-bit bwd', dict(w='split16', h='split16', cos='i8half', dpre='fp16s', w_bwd='fp16', h_bwd='fp16')),
-                ('x3: split fwd + 16-bit bwd, split W^T', dict(w='split16', h='split16', cos='i8half', dpre='fp16s', w_bwd='split16', h_bwd='fp16')),
+    x3 = dict(w='split16', h='split16', cos='i8half', dpre='fp16s', w_bwd='split16', h_bwd='fp16')
+    variants = [('x3 ideal decode', x3),
+                ('x3 fp16 decode', dict(x3, cos='i8half_k')),
+                ('x3 fp16 decode + double rounding', dict(x3, cos='i8half_k', dpre='fp16s2')),
+                ('x3 ideal decode + double rounding', dict(x3, dpre='fp16s2')),
+                ('x3 exact cos', dict(x3, cos='fp32')),
+                ('x3 exact cos, h_bwd fp32', dict(x3, cos='fp32', h_bwd='fp32')),
                 ]
     if os.environ.get('STUDY_ONLY'):
         variants = [v for v in variants if v[0].startswith(tuple(os.environ['STUDY_ONLY'].split(',')))]
