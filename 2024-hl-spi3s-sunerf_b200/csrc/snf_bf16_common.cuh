@@ -94,12 +94,14 @@ __device__ __forceinline__ uint32_t cosq_pack4(uint32_t t0, uint32_t t1, uint32_
 // (An fp16 decode was measured first: fp16 cannot tell 1 - q^2/T^2 from 1 for q <= 2 and rounds every cosine above 0.9998
 // to exactly 1 - the round-1 pile-up again, 16 times smaller; together with an fp16 x fp16 product it cost 4.5e-4 of
 // per-parameter gradient accuracy, against 1.1e-4 for this form.  tools/micro/bf16_grad_study.py, 'x3 fp16 decode'.)
-template <int B> __device__ __forceinline__ float cosq_dec(uint32_t w) {
+template <int B> __device__ __forceinline__ float cosq_dec_abs(uint32_t w) {   // |cos| of code B
   const uint32_t f = __byte_perm(w & 0x7F7F7F7Fu, 0x4B000000u, 0x7650 + B);
   const float q = __uint_as_float(f) - 8388608.f;
-  const float c = fmaf(q * q, -COSQ_INV_T2, 1.f);
-  const uint32_t sg = (B == 3 ? w : (w << (24 - 8 * B))) & 0x80000000u;   // code bit 7 -> sign bit
-  return __uint_as_float(__float_as_uint(c) ^ sg);
+  return fmaf(q * q, -COSQ_INV_T2, 1.f);
+}
+// the signs of codes 2 PR, 2 PR + 1 as the sign bits of an fp16 pair: XOR it into the packed products
+template <int PR> __device__ __forceinline__ uint32_t cosq_sign2(uint32_t w) {
+  return __byte_perm(w, 0u, PR == 0 ? 0x1404 : 0x3424) & 0x80008000u;
 }
 
 // One power-of-two scale per backward call keeps the fp16 dL/dpre images in range: S = 2^-ceil(log2(bound)) with

@@ -251,8 +251,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
       for (int k = 0; k < NQ; ++k)
         pv[k] = __ldcs(reinterpret_cast<const uint4 *>(img + (((sl * 4 + g * NQ + k) * TILE_M + row) << 4)));
     };
-    // (a0 c0, a1 c1) as an fp16 pair: the products are formed in fp32 and rounded once
-    auto mul2 = [&](float a0, float a1, float c0, float c1) { return pack_f16x2(a0 * c0, a1 * c1); };
+    // (a0 cos_0, a1 cos_1) as an fp16 pair for the codes 2 pr, 2 pr + 1 of the word w: the products with |cos| are formed in
+    // fp32 and rounded once, the two signs are flipped on the packed pair
+#define SNF_MUL2(a0, a1, w, pr) \
+    (pack_f16x2((a0) * cosq_dec_abs<2 * (pr)>(w), (a1) * cosq_dec_abs<2 * (pr) + 1>(w)) ^ cosq_sign2<pr>(w))
     // hand complete slabs to the MMA issuer first (ready barrier k, or none), then to the store warp (wrote[slot])
     auto publish = [&](int slot, int k) {
       fence_proxy_async_smem();
@@ -292,10 +294,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
             const uint4 &cv = pv[c >> 1];             // 8 codes of this chunk: two words
             const uint32_t cw0 = (c & 1) ? cv.z : cv.x, cw1 = (c & 1) ? cv.w : cv.y;
             uint4 o;
-            o.x = mul2(gg.x * wa0.x + gg.y * wb0.x, gg.x * wa0.y + gg.y * wb0.y, cosq_dec<0>(cw0), cosq_dec<1>(cw0));
-            o.y = mul2(gg.x * wa0.z + gg.y * wb0.z, gg.x * wa0.w + gg.y * wb0.w, cosq_dec<2>(cw0), cosq_dec<3>(cw0));
-            o.z = mul2(gg.x * wa1.x + gg.y * wb1.x, gg.x * wa1.y + gg.y * wb1.y, cosq_dec<0>(cw1), cosq_dec<1>(cw1));
-            o.w = mul2(gg.x * wa1.z + gg.y * wb1.z, gg.x * wa1.w + gg.y * wb1.w, cosq_dec<2>(cw1), cosq_dec<3>(cw1));
+            o.x = SNF_MUL2(gg.x * wa0.x + gg.y * wb0.x, gg.x * wa0.y + gg.y * wb0.y, cw0, 0);
+            o.y = SNF_MUL2(gg.x * wa0.z + gg.y * wb0.z, gg.x * wa0.w + gg.y * wb0.w, cw0, 1);
+            o.z = SNF_MUL2(gg.x * wa1.x + gg.y * wb1.x, gg.x * wa1.y + gg.y * wb1.y, cw1, 0);
+            o.w = SNF_MUL2(gg.x * wa1.z + gg.y * wb1.z, gg.x * wa1.w + gg.y * wb1.w, cw1, 1);
             *reinterpret_cast<uint4 *>(gA + sl * SLAB_BYTES + sw128_chunk_off(row, CHUNKS * g + c)) = o;
           }
           publish(sl, sl == 3 ? 0 : sl >= 4 ? sl - 3 : -1);
@@ -329,8 +331,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_dgr
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 const uint32_t w4 = cw[i >> 2];
-                pk[4 * c0 + i / 2] = mul2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]), cosq_dec<0>(w4), cosq_dec<1>(w4));
-                pk[4 * c0 + i / 2 + 1] = mul2(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]), cosq_dec<2>(w4), cosq_dec<3>(w4));
+                pk[4 * c0 + i / 2] = SNF_MUL2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]), w4, 0);
+                pk[4 * c0 + i / 2 + 1] = SNF_MUL2(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]), w4, 1);
               }
             };
             if (CPT == 32) {
