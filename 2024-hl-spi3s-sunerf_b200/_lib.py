@@ -72,6 +72,7 @@ _PROTOS = {
     'snf_error_string': (_c.c_char_p, [_I]),
     'snf_launch_count': (_L, []),
     'snf_count_launches': (None, [_L]),
+    'snf_config_reserve_sms': (_I, [_I]),
     'snf_stratified_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
     'snf_spherical_sample': (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _P, _P, _P]),
     'snf_hier_resample': (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),

@@ -21,6 +21,7 @@ struct DeviceState {
   std::once_flag once;
   int num_sms = 0;
   int status = 0;
+  int reserve = 0;   // SMs the persistent field-network grids leave free (snf_config_reserve_sms), atomic access
 };
 extern DeviceState g_devices[kMaxDevices];
 

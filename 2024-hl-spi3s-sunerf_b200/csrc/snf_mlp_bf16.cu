@@ -583,8 +583,24 @@ int snf_device_setup(int *num_sms_out) {
     d.num_sms = (err == cudaSuccess && n > 0) ? n : 148;
     d.status = snf_set_kernel_attributes();
   });
-  if (num_sms_out) *num_sms_out = d.num_sms;
+  if (num_sms_out) {
+    const int r = __atomic_load_n(&d.reserve, __ATOMIC_RELAXED);
+    int n = d.num_sms - r;
+    *num_sms_out = n >= 2 ? n : 2;
+  }
   return d.status;
+}
+
+// Multi-GPU training: the persistent field-network kernels fill every SM with one 224 KB CTA, so a concurrent NCCL kernel
+// finds no SM until a grid drains - and once its CTAs sit on a few SMs, spinning for the peer, the next persistent grid
+// cannot place its CTAs there.  Leaving a few SMs out of the persistent grids gives the collective a home of its own.
+extern "C" int snf_config_reserve_sms(int n) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= snf::kMaxDevices || n < 0 || n > 64) return SNF_E_ARG;
+  __atomic_store_n(&snf::g_devices[dev].reserve, n & ~1, __ATOMIC_RELAXED);   // whole CTA pairs
+  return 0;
 }
 
 int snf_bf16_set_attributes_bwd();   // snf_mlp_bf16_bwd.cu

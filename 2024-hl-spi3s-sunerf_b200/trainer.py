@@ -52,6 +52,13 @@ class RayTrainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        # multi-GPU schedule (measured on 2-8 GPUs): the coarse bucket is exchanged as soon as the coarse
+        # backward ends, on a few SMs the persistent grids leave free for NCCL's CTAs
+        import os
+        self.early_coarse_reduce = os.environ.get('SNF_EARLY_REDUCE', '1') == '1'
+        self.reserve_sms = int(os.environ.get('SNF_RESERVE_SMS', '4')) if self.world > 1 else 0
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().snf_config_reserve_sms(self.reserve_sms), 'snf_config_reserve_sms')
         self.step_count = 0
         self.lr0 = lr
         self._flatten()
@@ -254,7 +261,7 @@ class RayTrainer:
             ops.mlp_backward(q_c.view(-1, 4), w_c, g_raw_c.view(-1, 2), ws_c, gw, gb, packed_ptr=pk_c)
             # the coarse bucket is exchanged as soon as it exists (a millisecond before the fine backward ends): NCCL's
             # CTAs slot into the tails of the fine pass's persistent kernels instead of queueing up behind the step
-            h_coarse = self._reduce_async('coarse_model')
+            h_coarse = self._reduce_async('coarse_model') if self.early_coarse_reduce else None
         # ---- fine pass
         new_z, z_comb = r.sampler_hierarchical.resample(z, wts_c)
         Sf = z_comb.shape[1]
@@ -282,6 +289,8 @@ class RayTrainer:
         h_fine = self._reduce_async('fine_model')
         if side is not main:
             main.wait_stream(side)
+        if not self.early_coarse_reduce:
+            h_coarse = self._reduce_async('coarse_model')
         parallel.wait_all([h_coarse, h_fine])
         # ---- optimiser
         self._optimizer_step(device_sched)

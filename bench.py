@@ -186,8 +186,12 @@ def main():
     ap.add_argument('--ref-rays', type=int, default=RAYS_PER_GPU, help='rays per step of the reference arm (default: the full config batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial-backward', action='store_true', help='coarse backward after the fine one instead of beside it (A/B aid)')
+    ap.add_argument('--quick', action='store_true', help='headline step only (A/B aid): prints {"ms_per_step", "rays_per_s"} and exits')
     ap.add_argument('--no-cuda-graph', action='store_true', help='launch the ~30 kernels of a step one by one instead of replaying a graph')
     args = ap.parse_args()
+    if os.environ.get('SNF_BENCH_WATCHDOG'):        # developer aid: dump every thread's stack and exit if the run wedges
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['SNF_BENCH_WATCHDOG']), exit=True)
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
@@ -261,6 +265,17 @@ def main():
     l0 = ops.launch_count()
     ms = timed_loop(step_resident, args.steps)          # the headline: the step replayed as one CUDA graph (unless --no-cuda-graph)
     launches = ops.launch_count() - l0
+    if args.quick:
+        ms2 = timed_loop(step_resident, args.steps)
+        if rank == 0:
+            print(json.dumps({'ms_per_step': min(ms, ms2) / args.steps, 'rays_per_s': N * world * args.steps / (min(ms, ms2) * 1e-3),
+                              'n_gpus': world, 'early_reduce': trainer.early_coarse_reduce, 'reserve_sms': trainer.reserve_sms}), flush=True)
+        trainer._graph = None                  # a captured step holds NCCL work: release it before the communicator goes
+        del trainer
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier(); torch.distributed.destroy_process_group()
+        return
     # ---- roofline pass: the same K steps launched kernel by kernel, so that CUDA events can bracket the field-network
     #      launches on their stream (events cannot be read back from inside a replayed graph); same kernels, same data
     graphed = trainer.use_cuda_graph

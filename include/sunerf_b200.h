@@ -34,6 +34,12 @@ int64_t snf_launch_count(void);
 /* a CUDA-graph replay launches the captured kernels without passing through this library: the host adds them here */
 void snf_count_launches(int64_t n);
 
+/* Configuration of the CURRENT device (thread-safe, takes effect for later launches): the persistent field-network grids
+ * leave `n` SMs (rounded down to even, 0..64) free for a concurrent collective.  RayTrainer sets it when world_size > 1:
+ * it replaces nothing in the reference (Lightning 'dp' has no such notion), it is what lets the gradient exchange of
+ * run_emission.py:64-69 overlap the backward instead of queueing behind it.  Returns 0 or SNF_E_ARG. */
+int snf_config_reserve_sms(int n);
+
 /* ---- a1: StratifiedSampler.forward, sunerf/train/sampling.py:68-102 -------------------------------
  * t_vals[S] is the sampler buffer (linspace(0,1,S)); t_rand[N,S] is the torch.rand draw of :97, or NULL
  * for perturb=False.  Writes z_vals[N,S] and, if non-NULL, points[N,S,3].  Same fp32 operation order as
