@@ -9,12 +9,15 @@
 //
 // The activation pair does not fit next to the weight ring in shared memory (2 x 128 KB), so unlike the fused 16-bit
 // chain (snf_mlp_bf16.cu) this is ONE KERNEL PER LAYER over HBM-resident tile images:
-//   work item  = (128-point tile, N-half of 256 output features); persistent CTAs, item i -> CTA i mod grid, so the two
-//                halves of a tile run side by side on neighbouring CTAs (the A slabs of the second reader hit L2)
-//   warp 0     TMA producer: per k-slab one stage = A_hi, A_lo slabs (2 x 16 KB) + W_hi, W_lo blocks (2 x 32 KB) = 96 KB,
-//              two stages
-//   warp 1     MMA issuer: M = 128, N = 256, K = 16 per instruction, 3 instructions per k-step; accumulators double
-//              buffered in TMEM (2 x 256 columns), so the epilogue of item i runs under the MMAs of item i + 1
+//   work item  = (pair of 128-point tiles, N-half of 256 output features) per persistent CTA PAIR (cluster of 2, tcgen05
+//                cta_group::2): CTA r owns tile 2 tp + r - its A operand and its 128 accumulator lanes - and supplies
+//                half of every weight block, so a k-slab costs each SM 64 KB of L2 reads instead of the 96 KB of a
+//                single-CTA tile (the first version: L2-bound at 45 % of the tensor rate)
+//   warp 0     TMA producer: per k-slab one stage = A_hi, A_lo slabs (2 x 16 KB) + this CTA's halves of the W_hi, W_lo
+//              blocks (2 x 16 KB) = 64 KB, three stages
+//   warp 1     MMA issuer (leader CTA; the peer's warp 1 relays "my half of the stage has landed"): M = 256 across the
+//              pair, N = 256, K = 16 per instruction, 3 instructions per k-step; accumulators double buffered in TMEM
+//              (2 x 256 columns), so the epilogue of item i runs under the MMAs of item i + 1
 //   warps 4-11 epilogue: TMEM -> + bias -> sin / cos -> (hi, lo) pairs -> the next layer's tile images; in training also
 //              the saved fp16 activation image and the one-byte cosine code the 16-bit backward reads
 // sin / cos: two-constant Cody-Waite reduction to [-pi, pi] in fp32, then MUFU (absolute error 4e-7 there; the MUFU's
@@ -30,13 +33,13 @@ namespace snf {
 namespace bf {
 namespace x3 {
 
-constexpr int NST = 2;
-constexpr int STAGE_A = 2 * SLAB_BYTES;          // A_hi, A_lo
-constexpr int STAGE_B = 2 * WBLK_BYTES;          // W_hi, W_lo: 256 output features x 64 k each
-constexpr int STAGE_BYTES = STAGE_A + STAGE_B;   // 96 KB
-constexpr int OFF_BIAS = NST * STAGE_BYTES;      // 256 floats of this CTA's N-half
-constexpr int OFF_WOUT = OFF_BIAS + NCHUNK * 4;  // [2][256] floats of this CTA's N-half
-constexpr int OFF_BAR = OFF_WOUT + 2 * NCHUNK * 4;
+constexpr int NST = 3;
+constexpr int STAGE_A = 2 * SLAB_BYTES;          // A_hi, A_lo of this CTA's tile
+constexpr int STAGE_B = 2 * WHALF_BYTES;         // this CTA's halves (128 of 256 output features x 64 k) of W_hi, W_lo
+constexpr int STAGE_BYTES = STAGE_A + STAGE_B;   // 64 KB
+constexpr int OFF_BIAS = NST * STAGE_BYTES;      // [512] floats
+constexpr int OFF_WOUT = OFF_BIAS + D * 4;       // [2][512] floats
+constexpr int OFF_BAR = OFF_WOUT + 2 * D * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int N_EPI_W = 8;
 constexpr int THREADS = 128 + N_EPI_W * 32;
@@ -54,7 +57,7 @@ struct Params {
   int64_t codes_stride;
   const float *w_out;                  // last layer: [2][512], else null
   float2 *part;                        // last layer: [tiles * 128][4] partial outputs
-  int num_tiles;
+  int num_tiles;                       // even
 };
 
 // ---- positional encoding of [tiles * 128] rows (rows >= M encode x = 0) as the (hi, lo) layer-0 operand images.
@@ -117,96 +120,111 @@ __device__ __forceinline__ uint32_t cosq_enc_full(float c) {
   return c < 0.f ? (q | 0x80u) : q;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nh = blockIdx.x & 1;                       // the grid is even: a CTA always works on the same N-half
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   float *bias_s = reinterpret_cast<float *>(smem_raw + OFF_BIAS);
   float *wout_s = reinterpret_cast<float *>(smem_raw + OFF_WOUT);
   const uint32_t sBar = base + OFF_BAR;
-  auto bar_full = [&](int s) { return sBar + 8u * s; };
-  auto bar_empty = [&](int s) { return sBar + 8u * (NST + s); };
-  auto bar_accf = [&](int j) { return sBar + 8u * (2 * NST + j); };        // accumulator j complete (tcgen05.commit)
-  auto bar_acce = [&](int j) { return sBar + 8u * (2 * NST + 2 + j); };    // accumulator j drained (8 epilogue warps)
+  auto bar_full = [&](int s) { return sBar + 8u * s; };                    // leader: own TMA + the peer's relay
+  auto bar_empty = [&](int s) { return sBar + 8u * (NST + s); };           // multicast tcgen05.commit
+  auto bar_accf = [&](int j) { return sBar + 8u * (2 * NST + j); };        // accumulator j complete (multicast commit)
+  auto bar_acce = [&](int j) { return sBar + 8u * (2 * NST + 2 + j); };    // leader: accumulator j drained by the 16 epilogue warps of the pair
   const uint32_t tmem_slot = sBar + 8u * (2 * NST + 4);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int j = 0; j < 2; ++j) { mbar_init(bar_accf(j), 1); mbar_init(bar_acce(j), N_EPI_W); }
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_accf(j), 1); mbar_init(bar_acce(j), 2 * N_EPI_W); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < NCHUNK; i += THREADS) bias_s[i] = __ldg(p.bias + nh * NCHUNK + i);
+  for (int i = threadIdx.x; i < D; i += THREADS) bias_s[i] = __ldg(p.bias + i);
   if (p.w_out != nullptr)
-    for (int i = threadIdx.x; i < 2 * NCHUNK; i += THREADS)
-      wout_s[i] = __ldg(p.w_out + (i / NCHUNK) * D + nh * NCHUNK + (i % NCHUNK));
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < 2 * D; i += THREADS) wout_s[i] = __ldg(p.w_out + i);
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + OFF_BAR + 8 * (2 * NST + 4));
-  const int n_items = p.num_tiles * 2;
+  const int n_items = p.num_tiles;                     // (tile pairs) x (2 N-halves); item -> (tile pair item >> 1, N-half item & 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      // =========================== TMA producer
+      // =========================== TMA producer: this CTA's tile and its half of every weight block
       const uint64_t keep = l2_policy_evict_last();
       int s = 0; uint32_t ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int64_t tile = item >> 1;
+      for (int item = pair; item < n_items; item += npairs) {
+        const int64_t tile = (int64_t)(item >> 1) * 2 + rank;
+        const int nh = item & 1;
         const uint8_t *ah = p.a_hi + tile * p.a_hi_stride, *al = p.a_lo + tile * p.a_lo_stride;
         for (int ks = 0; ks < p.nslab; ++ks) {
           mbar_wait(bar_empty(s), ph ^ 1);
           mbar_arrive_expect_tx(bar_full(s), STAGE_BYTES);
           const uint32_t st = base + s * STAGE_BYTES;
-          const int64_t wb = (int64_t)(nh * p.nslab + ks) * WBLK_BYTES;
+          const int64_t wb = (int64_t)(nh * p.nslab + ks) * WBLK_BYTES + rank * WHALF_BYTES;
           bulk_g2s(st, ah + (int64_t)ks * SLAB_BYTES, SLAB_BYTES, bar_full(s));
           bulk_g2s(st + SLAB_BYTES, al + (int64_t)ks * SLAB_BYTES, SLAB_BYTES, bar_full(s));
-          bulk_g2s_hint(st + STAGE_A, p.w_hi + wb, WBLK_BYTES, bar_full(s), keep);
-          bulk_g2s_hint(st + STAGE_A + WBLK_BYTES, p.w_lo + wb, WBLK_BYTES, bar_full(s), keep);
+          bulk_g2s_hint(st + STAGE_A, p.w_hi + wb, WHALF_BYTES, bar_full(s), keep);
+          bulk_g2s_hint(st + STAGE_A + WHALF_BYTES, p.w_lo + wb, WHALF_BYTES, bar_full(s), keep);
           if (++s == NST) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer: uniform control flow, one elected lane issues
-    const uint32_t idesc = idesc_f16kind(TILE_M, NCHUNK, FMT_F16, FMT_F16);
-    int s = 0; uint32_t ph = 0, eph = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int j = it & 1;
-      if (it >= 2) { mbar_wait(bar_acce(j), (eph >> j) & 1u); eph ^= 1u << j; }   // the epilogue has drained this buffer
-      tcgen05_fence_after();
-      const uint32_t dcol = tmem + j * NCHUNK;
-      for (int ks = 0; ks < p.nslab; ++ks) {
-        mbar_wait(bar_full(s), ph);
+    int s = 0; uint32_t ph = 0;
+    if (rank == 0) {
+      // =========================== MMA issuer (leader CTA): uniform control flow, one elected lane issues
+      const uint32_t idesc = idesc_f16kind(2 * TILE_M, NCHUNK, FMT_F16, FMT_F16);
+      uint32_t eph = 0;
+      int it = 0;
+      for (int item = pair; item < n_items; item += npairs, ++it) {
+        const int j = it & 1;
+        if (it >= 2) { mbar_wait(bar_acce(j), (eph >> j) & 1u); eph ^= 1u << j; }   // both epilogues have drained this buffer
         tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t st = base + s * STAGE_BYTES;
-          const uint64_t ahi = smem_desc(st, 16, 1024), alo = smem_desc(st + SLAB_BYTES, 16, 1024);
-          const uint64_t bhi = smem_desc(st + STAGE_A, 16, 1024), blo = smem_desc(st + STAGE_A + WBLK_BYTES, 16, 1024);
-          const int nk = ks == p.nslab - 1 ? p.k16_last : 4;
-          for (int k4 = 0; k4 < nk; ++k4) {
-            mma_ss(dcol, ahi + 2 * k4, bhi + 2 * k4, idesc, (ks | k4) != 0);
-            mma_ss(dcol, ahi + 2 * k4, blo + 2 * k4, idesc, 1);
-            mma_ss(dcol, alo + 2 * k4, bhi + 2 * k4, idesc, 1);
+        const uint32_t dcol = tmem + j * NCHUNK;
+        for (int ks = 0; ks < p.nslab; ++ks) {
+          mbar_wait(bar_full(s), ph);                    // both CTAs' parts of the stage have landed
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t st = base + s * STAGE_BYTES;
+            const uint64_t ahi = smem_desc(st, 16, 1024), alo = smem_desc(st + SLAB_BYTES, 16, 1024);
+            const uint64_t bhi = smem_desc(st + STAGE_A, 16, 1024), blo = smem_desc(st + STAGE_A + WHALF_BYTES, 16, 1024);
+            const int nk = ks == p.nslab - 1 ? p.k16_last : 4;
+            for (int k4 = 0; k4 < nk; ++k4) {
+              mma_ss_2cta(dcol, ahi + 2 * k4, bhi + 2 * k4, idesc, (ks | k4) != 0);
+              mma_ss_2cta(dcol, ahi + 2 * k4, blo + 2 * k4, idesc, 1);
+              mma_ss_2cta(dcol, alo + 2 * k4, bhi + 2 * k4, idesc, 1);
+            }
+            mma_commit_2cta(bar_empty(s), 3);            // frees the stage in both CTAs
+            if (ks == p.nslab - 1) mma_commit_2cta(bar_accf(j), 3);
           }
-          mma_commit(bar_empty(s));
-          if (ks == p.nslab - 1) mma_commit(bar_accf(j));
+          __syncwarp();
+          if (++s == NST) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == NST) { s = 0; ph ^= 1; }
       }
+    } else if (lane == 0) {
+      // =========================== peer relay: tell the leader when this CTA's part of a stage has landed
+      for (int item = pair; item < n_items; item += npairs)
+        for (int ks = 0; ks < p.nslab; ++ks) {
+          mbar_wait(bar_full(s), ph);
+          mbar_arrive_remote_relaxed(mapa_shared(bar_full(s), 0));   // the data is TMA-written and tensor-core-read
+          if (++s == NST) { s = 0; ph ^= 1; }
+        }
     }
   } else if (warp >= 4) {
-    // =========================== epilogue: thread = (row, column half g of the 256-column accumulator)
+    // =========================== epilogue: thread = (row of this CTA's tile, column half g of the 256-column accumulator)
     const int e = warp - 4, q = warp & 3, g = e >> 2;
     const int row = q * 32 + lane;
     uint32_t fph = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const uint32_t acce_addr[2] = {rank == 0 ? bar_acce(0) : mapa_shared(bar_acce(0), 0),
+                                   rank == 0 ? bar_acce(1) : mapa_shared(bar_acce(1), 0)};
+    for (int item = pair; item < n_items; item += npairs, ++it) {
       const int j = it & 1;
-      const int64_t tile = item >> 1;
+      const int64_t tile = (int64_t)(item >> 1) * 2 + rank;
+      const int nh = item & 1;
       mbar_wait(bar_accf(j), (fph >> j) & 1u); fph ^= 1u << j;
       tcgen05_fence_after();
       const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16) + j * NCHUNK + g * 128;
@@ -222,13 +240,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p
         uint32_t(&nxt)[32] = (c & 1) ? accA : accB;
         tmem_ld_wait(cur);
         if (c + 1 < 4) tmem_ld32(tm_row + (c + 1) * 32, nxt);
-        const int nloc = g * 128 + c * 32;              // column inside this CTA's N-half
-        const int ncol = nh * NCHUNK + nloc;            // column of the 512-wide layer
+        const int ncol = nh * NCHUNK + g * 128 + c * 32;   // column of the 512-wide layer
         const int slab = ncol >> 6, c8_0 = (ncol & 63) >> 3;
         uint32_t hi[16], lo[16], cq[8];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 b = *reinterpret_cast<const float4 *>(bias_s + nloc + i);
+          const float4 b = *reinterpret_cast<const float4 *>(bias_s + ncol + i);
           const float bb[4] = {b.x, b.y, b.z, b.w};
           float sv[4], cv[4];
 #pragma unroll
@@ -242,8 +259,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p
           }
           if (cod != nullptr) cq[i / 4] = cosq_pack4(cosq_enc_full(cv[0]), cosq_enc_full(cv[1]), cosq_enc_full(cv[2]), cosq_enc_full(cv[3]));
           if (p.w_out != nullptr) {
-            const float4 wa = *reinterpret_cast<const float4 *>(wout_s + nloc + i);
-            const float4 wb = *reinterpret_cast<const float4 *>(wout_s + NCHUNK + nloc + i);
+            const float4 wa = *reinterpret_cast<const float4 *>(wout_s + ncol + i);
+            const float4 wb = *reinterpret_cast<const float4 *>(wout_s + D + ncol + i);
             o0 += sv[0] * wa.x + sv[1] * wa.y + sv[2] * wa.z + sv[3] * wa.w;
             o1 += sv[0] * wb.x + sv[1] * wb.y + sv[2] * wb.z + sv[3] * wb.w;
           }
@@ -270,13 +287,16 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce(j));
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(acce_addr[j]);
+        else mbar_arrive_remote_relaxed(acce_addr[j]);
+      }
       if (p.part != nullptr) p.part[(tile * TILE_M + row) * 4 + nh * 2 + g] = make_float2(o0, o1);
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  cluster_sync_all();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc_2cta(tmem, 512); }
 }
 
 // out[m] = ((p0 + p1) + (p2 + p3)) + b_out + offset: the four partial dot products of a point in a fixed order
@@ -314,7 +334,7 @@ extern "C" int snf_mlp_fwd_x3(const float *x, int64_t M, const void *packed, flo
   const uint8_t *pk = reinterpret_cast<const uint8_t *>(packed);
   bf::x3::x3_encode_kernel<<<(unsigned)ceil_div64(rows * 16, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(x), M, rows,
                                                                                 w.enc, w.enc_lo);
-  int grid = 2 * num_tiles < nsm ? 2 * num_tiles : nsm;
+  int grid = num_tiles < nsm ? num_tiles : nsm;     // CTA pairs: (num_tiles / 2) tile pairs x 2 N-halves = num_tiles items per pair slot
   grid &= ~1;
   for (int l = 0; l < bf::NH; ++l) {
     bf::x3::Params p{};

@@ -16,7 +16,8 @@ ks = []
 for r in rows[2:]:
     ks.append({'kernel': r[kn].split('(')[0], 'dram_read_bytes': float(r[rd]) * scale[units[rd]],
                'dram_write_bytes': float(r[wr]) * scale[units[wr]], 'duration_s': float(r[du]) * tscale[units[du]]})
-train = [k for k in ks if 'mlp_fwd_bf16_kernel<1>' in k['kernel'] or 'dgrad' in k['kernel'] or 'wgrad' in k['kernel']]
+is_train_fwd = lambda n: 'mlp_fwd_bf16_kernel' in n and not ('<0>' in n or '(bool)0' in n or 'false' in n)
+train = [k for k in ks if is_train_fwd(k['kernel']) or 'dgrad' in k['kernel'] or 'wgrad' in k['kernel']]
 doc = {'source': rep, 'kernels': ks,
        'train_step_mlp_traffic_bytes': sum(k['dram_read_bytes'] + k['dram_write_bytes'] for k in train),
        'train_step_mlp_kernels': len(train)}
