@@ -52,11 +52,13 @@ class RayTrainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        # multi-GPU schedule (measured on 2-8 GPUs): the coarse bucket is exchanged as soon as the coarse
-        # backward ends, on a few SMs the persistent grids leave free for NCCL's CTAs
+        # multi-GPU schedule switches.  Measured on 8 GPUs of one box against the 1-GPU step of the same
+        # box (3.40 ms): both buckets exchanged after the fine backward, no SM reserve - 3.57 ms (the default); coarse bucket
+        # exchanged early from the side stream on 4 SMs left free by the persistent grids - 3.79 ms: NCCL's CTAs that do not
+        # fit the reserve wait for a tail of the fine pass while their peers spin.  On 2 GPUs the variants are equal (3.53 ms).
         import os
-        self.early_coarse_reduce = os.environ.get('SNF_EARLY_REDUCE', '1') == '1'
-        self.reserve_sms = int(os.environ.get('SNF_RESERVE_SMS', '4')) if self.world > 1 else 0
+        self.early_coarse_reduce = os.environ.get('SNF_EARLY_REDUCE', '0') == '1'
+        self.reserve_sms = int(os.environ.get('SNF_RESERVE_SMS', '0')) if self.world > 1 else 0
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().snf_config_reserve_sms(self.reserve_sms), 'snf_config_reserve_sms')
         self.step_count = 0

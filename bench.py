@@ -176,6 +176,21 @@ def cpu_baseline(sample_rays=RAYS_PER_GPU, render_rays=RENDER_BATCH):
 
 
 # ------------------------------------------------------------------------------------------ this repo's arm
+def teardown(world):
+    """Destroy the NCCL communicator AFTER the line is printed; the measurements are complete by then, so a teardown that
+    raises or wedges (NCCL waits for every CUDA graph that captured the communicator) must not fail the run."""
+    if world <= 1:
+        return
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        torch.distributed.destroy_process_group()
+    except Exception as e:
+        print(f'[bench] process-group teardown: {e!r}', file=sys.stderr, flush=True)
+    t.cancel()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -274,7 +289,8 @@ def main():
         del trainer
         torch.cuda.synchronize()
         if world > 1:
-            torch.distributed.barrier(); torch.distributed.destroy_process_group()
+            torch.distributed.barrier()
+        teardown(world)
         return
     # ---- roofline pass: the same K steps launched kernel by kernel, so that CUDA events can bracket the field-network
     #      launches on their stream (events cannot be read back from inside a replayed graph); same kernels, same data
@@ -355,7 +371,8 @@ def main():
         nx = max(5, args.steps // 2)
         ms_x = timed_loop(step_x3, nx) / nx
         tx.check_finite()
-        del tx
+        tx._graph = None
+        del tx, step_x3
 
         def render_x3():
             with torch.no_grad():
@@ -400,6 +417,7 @@ def main():
 
     # ---- density-temperature config (DT_2012_11.yaml: NeRF_DT + AIA response head, 3072 rays, 7 channels, half of the
     #      rays with the STEREO channel mask) - reported next to the headline, same fast path
+    trainer._graph = None                  # closures above still hold the trainer: drop its captured step explicitly
     del trainer, rend, renderer
     torch.cuda.empty_cache()
     torch.manual_seed(7)
@@ -421,10 +439,14 @@ def main():
     ms_dt = timed_loop(step_dt, 5) / 5
     tr_dt.check_finite()
 
+    # a captured step holds NCCL work: release every graph before the communicator goes
+    tr_dt._graph = None
+    del tr_dt, step_dt, step_resident, step_e2e
+    torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
     if rank != 0:
+        teardown(world)
         return
     value = N * world * args.steps / (ms * 1e-3)
     e2e = N * world * args.steps / (ms_e2e * 1e-3)
@@ -481,6 +503,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line), flush=True)
+    teardown(world)
 
 
 if __name__ == '__main__':

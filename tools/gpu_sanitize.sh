@@ -9,7 +9,7 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$sel" > $
 tail -2 $out/san_plain.log
 extra=""
 [ "$tool" = racecheck ] && extra="--racecheck-report all"
-timeout 1300 compute-sanitizer --tool $tool $extra --log-file $out/sanitizer_$tool.log --print-limit 50 \
+timeout ${SAN_TIMEOUT:-600} compute-sanitizer --tool $tool $extra --log-file $out/sanitizer_$tool.log --print-limit 50 \
     python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$sel" > $out/san_$tool.pytest.log 2>&1
 echo "sanitizer($tool) rc=$?"
 tail -3 $out/san_$tool.pytest.log
