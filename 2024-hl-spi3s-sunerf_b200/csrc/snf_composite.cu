@@ -146,6 +146,126 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K5, S = 64 NC
+// Pair layout for the configs' sample counts (64 coarse, 192 = 64 + 128 fine): a chunk is 64 consecutive samples, lane l
+// owns samples 64 c + 2 l and 64 c + 2 l + 1.  Against the one-sample-per-lane kernels above that is half the
+// double-precision scans (one per 64 samples: the pair's product / sum is formed in registers first), half the neighbour
+// shuffles, no bounds predicates, and 8 / 16-byte loads and stores that a warp still issues fully coalesced.  The generic
+// kernels stay for every other S.  Same arithmetic per sample; the exclusive product is T_j = float(prod_{k<j} f_k) in
+// double with a different association (1e-16 before the rounding to float, as in the generic kernel's tree scan).
+template <int NC>
+struct PairRay {
+  float dz[2 * NC], E[2 * NC], a[2 * NC], P[2 * NC];
+  float rawy[2 * NC];
+};
+
+// loads of one ray (all issued before the first use), dz (emission.py:24-29), E, a and P = E T with the exclusive product T
+template <int NC>
+__device__ __forceinline__ void pair_ray_forward(const float2 *__restrict__ raw, const float *__restrict__ z, int64_t ray,
+                                                 int lane, float dnorm, PairRay<NC> &r) {
+  constexpr int S = 64 * NC;
+  float2 zz[NC];
+  float4 rw[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    zz[c] = __ldcs(reinterpret_cast<const float2 *>(z + ray * S) + c * 32 + lane);
+    rw[c] = __ldcs(reinterpret_cast<const float4 *>(raw + ray * S) + c * 32 + lane);
+  }
+  double carry = 1.0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float up = __shfl_up_sync(kFull, zz[c].y, 1);
+    const float prev31 = __shfl_sync(kFull, zz[c > 0 ? c - 1 : 0].y, 31);
+    const float d0 = lane > 0 ? fsub(zz[c].x, up) : (c > 0 ? fsub(zz[c].x, prev31) : fsub(zz[0].y, zz[0].x));
+    const float dz0 = fmul(d0, dnorm), dz1 = fmul(fsub(zz[c].y, zz[c].x), dnorm);
+    const float E0 = fmul(expf(rw[c].x), dz0), E1 = fmul(expf(rw[c].z), dz1);              // emission.py:34
+    const float a0 = expf(fmul(-fmaxf(rw[c].y, 0.f), dz0)), a1 = expf(fmul(-fmaxf(rw[c].w, 0.f), dz1));   // :37
+    const double f0 = (double)fadd(a0, 1e-10f), f1 = (double)fadd(a1, 1e-10f);             // :43
+    const double incl = warp_incl_prod(f0 * f1, lane);
+    double excl = shfl_up_d(incl, 1);
+    if (lane == 0) excl = 1.0;
+    const double t0 = carry * excl;
+    r.dz[2 * c] = dz0; r.dz[2 * c + 1] = dz1;
+    r.E[2 * c] = E0; r.E[2 * c + 1] = E1;
+    r.a[2 * c] = a0; r.a[2 * c + 1] = a1;
+    r.rawy[2 * c] = rw[c].y; r.rawy[2 * c + 1] = rw[c].w;
+    r.P[2 * c] = fmul(E0, (float)t0);                                                      // :46
+    r.P[2 * c + 1] = fmul(E1, (float)(t0 * f0));
+    carry *= __shfl_sync(kFull, incl, 31);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_emission_fwd_pair_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
+                                       const float *__restrict__ rays_d, int64_t N, float *__restrict__ image,
+                                       float *__restrict__ weights, float *__restrict__ absorption) {
+  constexpr int S = 64 * NC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
+  const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));          // :29
+  PairRay<NC> r;
+  pair_ray_forward<NC>(raw, z, ray, lane, dnorm, r);
+  double isum = 0.0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    __stcs(reinterpret_cast<float2 *>(absorption + ray * S) + c * 32 + lane, make_float2(r.a[2 * c], r.a[2 * c + 1]));
+    isum += (double)r.P[2 * c] + (double)r.P[2 * c + 1];
+  }
+  const float I = (float)warp_sum(isum);                                                   // :48
+  if (lane == 0) image[ray] = I;
+  const float den = fadd(I, 1e-10f);
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    __stcs(reinterpret_cast<float2 *>(weights + ray * S) + c * 32 + lane,
+           make_float2(fdiv(r.P[2 * c], den), fdiv(r.P[2 * c + 1], den)));                 // :51-52
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRayWarps * 32)
+    composite_emission_bwd_pair_kernel(const float2 *__restrict__ raw, const float *__restrict__ z,
+                                       const float *__restrict__ rays_d, int64_t N, const float *__restrict__ g_image,
+                                       const float *__restrict__ g_abs, float2 *__restrict__ g_raw) {
+  constexpr int S = 64 * NC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp;
+  if (ray >= N) return;
+  float2 ga_in[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    ga_in[c] = g_abs != nullptr ? __ldcs(reinterpret_cast<const float2 *>(g_abs + ray * S) + c * 32 + lane) : make_float2(0.f, 0.f);
+  const float d0 = rays_d[3 * ray], d1 = rays_d[3 * ray + 1], d2 = rays_d[3 * ray + 2];
+  const float dnorm = __fsqrt_rn(sum3(fmul(d0, d0), fmul(d1, d1), fmul(d2, d2)));
+  const float g = g_image[ray];
+  PairRay<NC> r;
+  pair_ray_forward<NC>(raw, z, ray, lane, dnorm, r);
+  // reverse pass: exclusive suffix sums of P (fp32, as in the generic kernel)
+  float rcarry = 0.f;
+#pragma unroll
+  for (int c = NC - 1; c >= 0; --c) {
+    const float P0 = r.P[2 * c], P1 = r.P[2 * c + 1];
+    float suf = P0 + P1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float n = __shfl_down_sync(kFull, suf, d);
+      if (lane + d < 32) suf += n;
+    }
+    suf += rcarry;                                   // inclusive of this lane's pair
+    const float ex1 = suf - (P0 + P1), ex0 = ex1 + P1;   // sum_{k > j} P_k for the pair's second / first sample
+    const float a0 = r.a[2 * c], a1 = r.a[2 * c + 1];
+    const float ga0 = g * ex0 / fadd(a0, 1e-10f) + ga_in[c].x, ga1 = g * ex1 / fadd(a1, 1e-10f) + ga_in[c].y;
+    float4 o;
+    o.x = g * P0;
+    o.y = r.rawy[2 * c] > 0.f ? -ga0 * r.dz[2 * c] * a0 : 0.f;
+    o.z = g * P1;
+    o.w = r.rawy[2 * c + 1] > 0.f ? -ga1 * r.dz[2 * c + 1] * a1 : 0.f;
+    __stcs(reinterpret_cast<float4 *>(g_raw + ray * S) + c * 32 + lane, o);
+    rcarry = __shfl_sync(kFull, suf, 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K6
 struct DtTables {
   float x[SNF_TABLE_LEN];
@@ -565,6 +685,16 @@ extern "C" int snf_composite_emission_fwd(const float *raw, const float *z, cons
   if (S > 256) return SNF_E_SHAPE;
   const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
   const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
+  // pair layout for S = 64, 128, 192, 256 (rows are then 256-byte multiples: vector accesses need the bases aligned)
+  if (S % 64 == 0 && ((reinterpret_cast<uintptr_t>(raw) & 15) | (reinterpret_cast<uintptr_t>(z) & 7) |
+                      (reinterpret_cast<uintptr_t>(weights) & 7) | (reinterpret_cast<uintptr_t>(absorption) & 7)) == 0) {
+#define SNF_LAUNCH_P(NC) \
+  composite_emission_fwd_pair_kernel<NC><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, image, weights, absorption)
+    switch (S / 64) { case 1: SNF_LAUNCH_P(1); break; case 2: SNF_LAUNCH_P(2); break; case 3: SNF_LAUNCH_P(3); break; default: SNF_LAUNCH_P(4); break; }
+#undef SNF_LAUNCH_P
+    count_launch();
+    return launch_status();
+  }
 #define SNF_LAUNCH(NCH) \
   composite_emission_fwd_kernel<NCH><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, S, image, weights, absorption)
   switch ((S + 31) / 32) {
@@ -587,6 +717,15 @@ extern "C" int snf_composite_emission_bwd(const float *raw, const float *z, cons
   const unsigned grid = (unsigned)ceil_div64(N, kRayWarps);
   const float2 *raw2 = reinterpret_cast<const float2 *>(raw);
   float2 *g2 = reinterpret_cast<float2 *>(g_raw);
+  if (S % 64 == 0 && ((reinterpret_cast<uintptr_t>(raw) & 15) | (reinterpret_cast<uintptr_t>(z) & 7) |
+                      (reinterpret_cast<uintptr_t>(g_raw) & 15) | (reinterpret_cast<uintptr_t>(g_absorption) & 7)) == 0) {
+#define SNF_LAUNCH_P(NC) \
+  composite_emission_bwd_pair_kernel<NC><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, g_image, g_absorption, g2)
+    switch (S / 64) { case 1: SNF_LAUNCH_P(1); break; case 2: SNF_LAUNCH_P(2); break; case 3: SNF_LAUNCH_P(3); break; default: SNF_LAUNCH_P(4); break; }
+#undef SNF_LAUNCH_P
+    count_launch();
+    return launch_status();
+  }
 #define SNF_LAUNCH(NCH) \
   composite_emission_bwd_kernel<NCH><<<grid, kRayWarps * 32, 0, (cudaStream_t)stream>>>(raw2, z, rays_d, N, S, g_image, g_absorption, g2)
   switch ((S + 31) / 32) {

@@ -97,3 +97,32 @@ def test_world2_replicas_stay_identical_in_tensor_core_mode_and_survive_an_empty
     assert np.isfinite(flat0).all()
     assert np.array_equal(flat0, flat1)
     assert np.array_equal(np.load(tmp_path / 'grad_0.npy'), np.load(tmp_path / 'grad_1.npy'))
+
+
+def test_single_process_data_parallel_render_from_a_thread_pool():
+    """The reference's own render path: ONE process, `nn.DataParallel(rendering)` over the visible GPUs, batches submitted
+    from a ThreadPoolExecutor (sunerf/evaluation/loader.py:37-39, 143-144, 226-229).  The opt-in shared-memory attributes and
+    the SM count are per-device state; the tensor-core mode on device 1 of the same process must give the bits device 0
+    gives (each ray is independent of its neighbours in the batch, so the scatter does not change a value)."""
+    _need2()
+    from concurrent.futures import ThreadPoolExecutor
+    import sunerf_b200 as s
+    for precision in ('bf16', 'x3'):
+        torch.manual_seed(3)
+        r = s.EmissionRadiativeTransfer(Rs_per_ds=1, model_config={'precision': precision}).cuda(0)
+        r.sampler.perturb = False
+        dp = torch.nn.DataParallel(r, device_ids=[0, 1])
+        batches = [{k: v.cuda(0) for k, v in s.rays.synthetic_rays(515 + 128 * i, seed=40 + i).items()} for i in range(4)]
+
+        def render(b, module):
+            with torch.no_grad():
+                return module(b['rays_o'], b['rays_d'], b['times'])['fine_image']
+
+        alone = [render(b, r).cpu() for b in batches]
+        with ThreadPoolExecutor(max_workers=3) as ex:
+            together = list(ex.map(lambda b: render(b, dp), batches * 2))
+        for d in range(2):
+            torch.cuda.synchronize(d)
+        for i, img in enumerate(together):
+            assert img.device.index == 0
+            assert torch.equal(img.cpu(), alone[i % len(batches)]), (precision, i)
