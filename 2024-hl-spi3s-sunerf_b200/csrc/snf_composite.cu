@@ -596,6 +596,8 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // true when table_x is the 0.05-step grid the arithmetic segment guess assumes (within 2e-3: the guess is then off by at
 // most one segment); every thread of the CTA must call it
 __device__ __forceinline__ bool dt_grid_is_uniform(const DtTables *t) {
@@ -718,9 +720,11 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   const bool uniform = dt_grid_is_uniform(tab);
   const uint32_t x_s = (uint32_t)__cvta_generic_to_shared(&tabs.x[0]);
   const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(&tabs.ys[0][0]);
+  const uint32_t kappa_s = (uint32_t)__cvta_generic_to_shared(&tabs.kappa[0]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float vc = vol_c[0];
-  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += (int64_t)gridDim.x * kRayWarps) {
+  const int64_t stride = (int64_t)gridDim.x * kRayWarps;
+  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += stride) {
     float2 zz[NC];
     float4 v[NC];
 #pragma unroll
@@ -729,7 +733,16 @@ __global__ void __launch_bounds__(kRayWarps * 32)
       v[c] = __ldcs(reinterpret_cast<const float4 *>(inf + ray * S) + c * 32 + lane);
     }
     const int k_lane = lane < C ? dt_channel(__ldg(wavelengths + ray * C + lane)) : -1;   // lane c: table row of channel c
-    const float nk_lane = k_lane >= 0 ? -tab->kappa[k_lane] * 1.4426950408889634f : 0.f;  // exp(-kappa B/2) = 2^(nk B/2)
+    if (ray + stride < N) {   // this warp's next ray on its way into L1 while this one is computed (the kernel is issue-bound;
+                              // ncu showed 12-17 % of the samples waiting for the first load of a ray)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        prefetch_l1(reinterpret_cast<const float2 *>(z + (ray + stride) * S) + c * 32 + lane);
+        prefetch_l1(reinterpret_cast<const float4 *>(inf + (ray + stride) * S) + c * 32 + lane);
+      }
+      if (lane == 0) prefetch_l1(wavelengths + (ray + stride) * C);
+    }
+    const float nk_lane = k_lane >= 0 ? -lds_f32(kappa_s + 4 * k_lane) * 1.4426950408889634f : 0.f;  // exp(-kappa B/2) = 2^(nk B/2)
     double qsum = 0.0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -787,10 +800,13 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   const bool uniform = dt_grid_is_uniform(tab);
   const uint32_t x_s = (uint32_t)__cvta_generic_to_shared(&tabs.x[0]);
   const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(&tabs.ys[0][0]);
+  const uint32_t kappa_s = (uint32_t)__cvta_generic_to_shared(&tabs.kappa[0]);
+  const uint32_t kon_s = (uint32_t)__cvta_generic_to_shared(&tabs.kappa_on[0]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float vc = vol_c[0];
   float gvc = 0.f;               // per-lane partial of dL/dvol_c, reduced once at the end
-  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += (int64_t)gridDim.x * kRayWarps) {
+  const int64_t stride = (int64_t)gridDim.x * kRayWarps;
+  for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += stride) {
     float2 zz[NC], greg[NC];
     float4 v[NC];
 #pragma unroll
@@ -801,7 +817,16 @@ __global__ void __launch_bounds__(kRayWarps * 32)
     }
     const int k_lane = lane < C ? dt_channel(__ldg(wavelengths + ray * C + lane)) : -1;
     const float gi_lane = lane < C ? __ldg(g_image + ray * C + lane) : 0.f;
-    const float kap_lane = k_lane >= 0 ? tab->kappa[k_lane] : 0.f;
+    if (ray + stride < N) {   // this warp's next ray on its way into L1 while this one is computed
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        prefetch_l1(reinterpret_cast<const float2 *>(z + (ray + stride) * S) + c * 32 + lane);
+        prefetch_l1(reinterpret_cast<const float4 *>(inf + (ray + stride) * S) + c * 32 + lane);
+        if (g_regq != nullptr) prefetch_l1(reinterpret_cast<const float2 *>(g_regq + (ray + stride) * S) + c * 32 + lane);
+      }
+      if (lane == 0) { prefetch_l1(wavelengths + (ray + stride) * C); prefetch_l1(g_image + (ray + stride) * C); }
+    }
+    const float kap_lane = k_lane >= 0 ? lds_f32(kappa_s + 4 * k_lane) : 0.f;
     DtPairRay<NC> r;
     dt_pair_setup<NC>(r, tab, x_s, ys_s, uniform, zz, v, lane);
     // per sample, summed over the channels: s1 = sum_c Gc u_c (u = w tau), dth = dL/dtheta, dB = dL/dB
@@ -842,7 +867,7 @@ __global__ void __launch_bounds__(kRayWarps * 32)
       const float t = warp_sum8(dkc, lane);
       const int ch = (lane >> 2) & 7;
       const int k = __shfl_sync(kFull, k_lane, ch);
-      if ((lane & 3) == 0 && k >= 0 && t != 0.f && tab->kappa_on[k] != 0.f) atomicAdd(&blk_acc[k], t);
+      if ((lane & 3) == 0 && k >= 0 && t != 0.f && lds_f32(kon_s + 4 * k) != 0.f) atomicAdd(&blk_acc[k], t);
     }
     // G_i = sum_{k>=i} dL/dB_k = dL/d term_i, term_i = dz_i (rho_i + rho_{i+1}): one suffix scan per chunk for all channels
     float G[2 * NC];

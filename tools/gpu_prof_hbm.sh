@@ -7,11 +7,12 @@ timeout 120 python tools/bench_hbm_kernels.py --only $only --iters 3 > gpurun_ou
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s 4 -c 2 -o /tmp/prof_hbm_$tag -f \
     python tools/bench_hbm_kernels.py --only $only --iters 3 > gpurun_out/ncu_hbm_$tag.log 2>&1
 python tools/ncu_summary.py /tmp/prof_hbm_$tag.ncu-rep 25 > gpurun_out/ncu_hbm_summary_$tag.txt 2>&1
-ncu -i /tmp/prof_hbm_$tag.ncu-rep --page raw --csv 2>/dev/null | python - <<'P' >> gpurun_out/ncu_hbm_summary_$tag.txt
-import csv, sys
-rows = list(csv.reader(sys.stdin))
+ncu -i /tmp/prof_hbm_$tag.ncu-rep --page raw --csv > /tmp/prof_hbm_$tag.csv 2>/dev/null
+python - /tmp/prof_hbm_$tag.csv <<'P' >> gpurun_out/ncu_hbm_summary_$tag.txt
+import csv, sys, io
+rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
-want = ['smsp__inst_executed.sum', 'sm__inst_executed_pipe_xu', 'sm__inst_executed_pipe_fp64', 'sm__inst_executed_pipe_lsu', 'sm__inst_executed_pipe_alu',
+want = ['smsp__inst_executed.sum', 'smsp__inst_executed.avg', 'sm__inst_executed.avg.per_cycle_elapsed', 'sm__throughput', 'smsp__inst_issued', 'sm__inst_executed_pipe', 'sm__inst_executed_pipe_xu', 'sm__inst_executed_pipe_fp64', 'sm__inst_executed_pipe_lsu', 'sm__inst_executed_pipe_alu',
         'sm__inst_executed_pipe_fma', 'smsp__issue_active.avg.pct', 'sm__warps_active.avg.pct_of_peak', 'smsp__cycles_active.avg',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared', 'sm__pipe_fp64_cycles_active', 'sm__pipe_xu_cycles_active', 'smsp__inst_executed_pipe_uniform']
 print('== counters')
@@ -21,4 +22,4 @@ for r in rows[2:]:
         if any(h.startswith(w) for w in want):
             print(f'   {h} = {r[i]} {rows[1][i]}')
 P
-head -70 gpurun_out/ncu_hbm_summary_$tag.txt | cut -c1-200
+grep -A60 '== counters' gpurun_out/ncu_hbm_summary_$tag.txt | cut -c1-160; head -64 gpurun_out/ncu_hbm_summary_$tag.txt | cut -c1-170
