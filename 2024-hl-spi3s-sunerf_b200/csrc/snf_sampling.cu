@@ -46,6 +46,19 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
   }
   if (hit == hit) my_far = hit;                                                   // :87-88 / :37-38
   const int nr = (int)(N - ray0 < rpw ? N - ray0 : rpw);
+  // S == 32 NJ: this lane's bin positions t[j-1], t[j], t[j+1] and their complements are the same for every ray of the
+  // warp - loaded once, not once per ray (a fifth of the instructions of a ray)
+  float tv[NJ > 0 ? NJ : 1][3], tc[NJ > 0 ? NJ : 1][3];
+  if constexpr (NJ > 0) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int j = min(max(k * 32 + lane + q - 1, 0), S - 1);
+        tv[k][q] = __ldg(t_vals + j);
+        tc[k][q] = fsub(1.f, tv[k][q]);
+      }
+  }
   auto do_ray = [&](int r, const float (&tr)[NJ > 0 ? NJ : 1]) {
     const float z_near = __shfl_sync(kFull, my_near, r), z_far = __shfl_sync(kFull, my_far, r);
     const float p0 = __shfl_sync(kFull, o0, r), p1 = __shfl_sync(kFull, o1, r), p2 = __shfl_sync(kFull, o2, r);
@@ -55,13 +68,7 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
       return fadd(fmul(z_near, fsub(1.f, t)), fmul(z_far, t));
     };
     const int64_t row = (ray0 + r) * S;
-    auto sample = [&](int j, float trj) {
-      float z = bin_edge(j);
-      if (t_rand != nullptr) {                                                    // :93-98
-        const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
-        const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
-        z = fadd(lo, fmul(fsub(hi, lo), trj));
-      }
+    auto finish = [&](int j, float z) {
       __stcs(z_out + row + j, z);
       if (pts_out != nullptr) {                                                   // :100
         pts_out[3 * (row + j)] = fadd(p0, fmul(e0, z));
@@ -69,9 +76,29 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
         pts_out[3 * (row + j) + 2] = fadd(p2, fmul(e2, z));
       }
     };
-    if (NJ > 0) {
+    auto sample = [&](int j, float trj) {
+      float z = bin_edge(j);
+      if (t_rand != nullptr) {                                                    // :93-98
+        const float hi = (j < S - 1) ? fmul(.5f, fadd(bin_edge(j + 1), z)) : z;
+        const float lo = (j > 0) ? fmul(.5f, fadd(z, bin_edge(j - 1))) : z;
+        z = fadd(lo, fmul(fsub(hi, lo), trj));
+      }
+      finish(j, z);
+    };
+    if constexpr (NJ > 0) {
 #pragma unroll
-      for (int k = 0; k < NJ; ++k) sample(k * 32 + lane, tr[k]);
+      for (int k = 0; k < NJ; ++k) {
+        const int j = k * 32 + lane;
+        float z = fadd(fmul(z_near, tc[k][1]), fmul(z_far, tv[k][1]));            // :90
+        if (t_rand != nullptr) {                                                  // :93-98
+          const float zn = fadd(fmul(z_near, tc[k][2]), fmul(z_far, tv[k][2]));
+          const float zp = fadd(fmul(z_near, tc[k][0]), fmul(z_far, tv[k][0]));
+          const float hi = (j < S - 1) ? fmul(.5f, fadd(zn, z)) : z;
+          const float lo = (j > 0) ? fmul(.5f, fadd(z, zp)) : z;
+          z = fadd(lo, fmul(fsub(hi, lo), tr[k]));
+        }
+        finish(j, z);
+      }
     } else {
       for (int j = lane; j < S; j += 32) sample(j, t_rand != nullptr ? __ldcs(t_rand + row + j) : 0.f);
     }
