@@ -195,8 +195,10 @@ class RayTrainer:
         """A rank whose shard of a (tail) batch is empty still joins both all-reduces - with zero gradients - and applies the
         same optimiser step as everybody else, so the replicas stay identical and nobody hangs in NCCL."""
         self.flat_grad.zero_()
-        # same issue order as _step_impl: coarse bucket first
-        parallel.wait_all([self._reduce_async('coarse_model'), self._reduce_async('fine_model')])
+        # the SAME issue order as _step_impl on the ranks that have rays (collectives pair up by order, and the two buckets
+        # have the same size: a swapped order would silently add fine gradients to coarse ones)
+        order = ('coarse_model', 'fine_model') if self.early_coarse_reduce else ('fine_model', 'coarse_model')
+        parallel.wait_all([self._reduce_async(name) for name in order])
         self._optimizer_step(self._device_sched)
         self._host_bookkeeping()
         nan = torch.full((4,), float('nan'), device=self.dev)
