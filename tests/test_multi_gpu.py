@@ -99,6 +99,7 @@ def test_world2_replicas_stay_identical_in_tensor_core_mode_and_survive_an_empty
     assert np.array_equal(np.load(tmp_path / 'grad_0.npy'), np.load(tmp_path / 'grad_1.npy'))
 
 
+@pytest.mark.timeout(420)
 def test_single_process_data_parallel_render_from_a_thread_pool():
     """The reference's own render path: ONE process, `nn.DataParallel(rendering)` over the visible GPUs, batches submitted
     from a ThreadPoolExecutor (sunerf/evaluation/loader.py:37-39, 143-144, 226-229).  The opt-in shared-memory attributes and
