@@ -26,7 +26,9 @@ from . import rays, parallel, image_render, checkpoint, ray_store
 from .ray_store import RayStore
 from .image_render import ObserverRenderer
 from .fused import FusedRender
+from .parallel import ReplicatedRendering
 
 __all__ = ['SnfError', 'build', 'ops', 'NeRF', 'NeRF_DT', 'EmissionModel', 'PositionalEncoding', 'Sine', 'SimpleStar',
            'StratifiedSampler', 'SphericalSampler', 'HierarchicalSampler', 'SuNeRFRendering', 'EmissionRadiativeTransfer',
-           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore', 'FusedRender']
+           'DensityTemperatureRadiativeTransfer', 'RayTrainer', 'ImageAsinhScaling', 'ObserverRenderer', 'RayStore', 'FusedRender',
+           'ReplicatedRendering']

@@ -62,3 +62,74 @@ def wait_all(handles: List) -> None:
     for h in handles:
         if h is not None:
             h.wait()
+
+
+class ReplicatedRendering(torch.nn.Module):
+    """Single-process rendering over several GPUs with the call surface of `nn.DataParallel(rendering)` (the reference's
+    render path, sunerf/evaluation/loader.py:37-39,143-144): rays are split along dim 0, every device renders its share
+    with ITS OWN resident copy of the module, the outputs are concatenated on the first device.  No collective and no
+    per-call parameter broadcast - `nn.DataParallel` re-replicates the module on every forward through an NCCL broadcast,
+    which deadlocks on torch 2.11 / NCCL 2.28 as soon as two threads enter it at once, exactly what the reference's
+    thread-pool render loop (loader.py:226-229) does.  Safe to call from several threads; `sync_weights()` after the
+    parameters of `rendering` changed (training, load_state_dict)."""
+
+    def __init__(self, rendering: torch.nn.Module, device_ids: Optional[List[int]] = None):
+        super().__init__()
+        import copy
+        if device_ids is None:
+            device_ids = list(range(torch.cuda.device_count()))
+        src = next(rendering.parameters()).device
+        if src.type != 'cuda' or src.index != device_ids[0]:
+            raise ValueError(f'the rendering module must live on the first device (cuda:{device_ids[0]}), it is on {src}')
+        self.device_ids = list(device_ids)
+        self.module = rendering
+        self.replicas = torch.nn.ModuleList([copy.deepcopy(rendering).to(torch.device('cuda', d)) for d in device_ids[1:]])
+
+    @torch.no_grad()
+    def sync_weights(self) -> None:
+        sd = self.module.state_dict()
+        for rep in self.replicas:
+            rep.load_state_dict(sd)          # copy_ in place: the replicas' packed weight images notice the new version
+
+    def forward(self, *inputs, **kwargs):
+        import threading
+        n = inputs[0].shape[0]
+        mods = [self.module] + list(self.replicas)
+        world = min(len(mods), max(n, 1))
+        if world == 1:
+            return self.module(*inputs, **kwargs)
+        dev0 = torch.device('cuda', self.device_ids[0])
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev0))           # the inputs as the caller's stream produced them
+        grad = torch.is_grad_enabled()
+        results, errors = [None] * world, [None] * world
+
+        def work(i):
+            dev = torch.device('cuda', self.device_ids[i])
+            sl = shard_rows(n, i, world)
+            try:
+                with torch.cuda.device(dev), torch.set_grad_enabled(grad):
+                    st = torch.cuda.current_stream(dev)
+                    st.wait_event(ready)
+                    move = lambda t: t[sl].to(dev, non_blocking=True) if torch.is_tensor(t) and t.dim() > 0 and t.shape[0] == n else t
+                    out = mods[i](*[move(t) for t in inputs], **{k: move(v) for k, v in kwargs.items()})
+                    out = {k: v.to(dev0, non_blocking=True) for k, v in out.items()}      # stream-ordered peer copies
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    results[i] = (out, done)
+            except BaseException as e:  # noqa: BLE001  (re-raised in the caller's thread)
+                errors[i] = e
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(1, world)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        cur = torch.cuda.current_stream(dev0)
+        for _, done in results:
+            cur.wait_event(done)
+        return {k: torch.cat([r[0][k] for r in results], dim=0) for k in results[0][0]}
