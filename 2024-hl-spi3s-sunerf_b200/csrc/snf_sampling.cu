@@ -158,13 +158,19 @@ __device__ __forceinline__ void warp_prefix_counts(const int *cnt, int n, int la
   for (int i = 0; i < PER; ++i) out[i] += excl;
 }
 
-template <int PER>   // PER = ceil(n_new / 32): new samples per lane (consecutive k)
+// PER = ceil(n_new / 32): new samples per lane (consecutive k).  SC, NC > 0: the sample counts as compile-time constants
+// (the configs' 64 -> +128 on the shared u grid): every loop below has a known trip count and unrolls, the bounds tests
+// and most of the index arithmetic fold away - the kernel is bound by instruction issue, a third of it was loop control.
+#define SNF_UNROLL_IF_CT _Pragma("unroll (SC > 0 ? 8 : 1)")
+template <int PER, int SC = 0, int NC = 0, int UPR = -1>
 __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_vals,
                                                    const float *__restrict__ weights,
                                                    const float *__restrict__ u, const float *__restrict__ cdf_in,
-                                                   int64_t N, int S, int n_new, float *__restrict__ new_z,
+                                                   int64_t N, int S_rt, int n_new_rt, float *__restrict__ new_z,
                                                    float *__restrict__ z_comb, int64_t *__restrict__ inds,
-                                                   float *__restrict__ cdf_out, int u_per_ray) {
+                                                   float *__restrict__ cdf_out, int u_per_ray_rt) {
+  const int S = SC > 0 ? SC : S_rt, n_new = NC > 0 ? NC : n_new_rt;
+  const int u_per_ray = UPR >= 0 ? UPR : u_per_ray_rt;
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -184,22 +190,29 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   const int nc = S - 1;  // CDF length == number of bin centres
   if (u_per_ray) {
     us = reinterpret_cast<float *>(cnt + ncnt);
+    SNF_UNROLL_IF_CT
     for (int k = lane; k < n_new; k += 32) us[k] = __ldcs(u + ray * n_new + k);
   }
 
+  SNF_UNROLL_IF_CT
   for (int j = lane; j < S; j += 32) zs[j] = __ldcs(z_vals + ray * S + j);
+  SNF_UNROLL_IF_CT
   for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;
   __syncwarp();
+  SNF_UNROLL_IF_CT
   for (int j = lane; j < nc; j += 32) bins[j] = fmul(.5f, fadd(zs[j + 1], zs[j]));   // :118
   if (cdf_in != nullptr) {
+    SNF_UNROLL_IF_CT
     for (int j = lane; j < nc; j += 32) cdf[j] = cdf_in[ray * nc + j];
   } else {
     const float *w = weights + ray * S + 1;  // weights[..., 1:-1]  :119
     const int nw = S - 2;
     double part = 0.0;
+    SNF_UNROLL_IF_CT
     for (int j = lane; j < nw; j += 32) part += (double)fadd(__ldcs(w + j), 1e-5f);
     const float total = (float)warp_sum(part);                                       // :134
     double carry = 0.0;
+    SNF_UNROLL_IF_CT
     for (int base = 0; base < nw; base += 32) {                                      // :137
       const int j = base + lane;
       const double p = (j < nw) ? (double)fdiv(fadd(w[j], 1e-5f), total) : 0.0;
@@ -211,10 +224,12 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   }
   __syncwarp();
   if (cdf_out != nullptr)
+    SNF_UNROLL_IF_CT
     for (int j = lane; j < nc; j += 32) cdf_out[ray * nc + j] = cdf[j];
 
   // ---- first[j] = #{k : u_k < cdf_j} and its histogram (ascending shared u only)
   if (!u_per_ray)
+  SNF_UNROLL_IF_CT
   for (int j = lane; j < nc; j += 32) {
     const float c = cdf[j];
     int k0 = __float2int_ru(c * (float)(n_new - 1));        // exact on the ideal grid k / (n - 1); NaN -> 0
@@ -245,6 +260,7 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
     }
   }
   __syncwarp();
+  SNF_UNROLL_IF_CT
   for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;         // reused for the merge below
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
@@ -263,15 +279,19 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
     }
   }
   __syncwarp();
+  SNF_UNROLL_IF_CT
   for (int k = lane; k < n_new; k += 32) __stcs(new_z + ray * n_new + k, nz[k]);     // coalesced copy of the row
 
   // ---- sort(cat(z, new_z))  :123
   bool sorted = true;
+  SNF_UNROLL_IF_CT
   for (int j = lane; j < S - 1; j += 32) sorted &= (zs[j] <= zs[j + 1]);
+  SNF_UNROLL_IF_CT
   for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
   sorted = __all_sync(kFull, sorted) && !u_per_ray;        // first[] exists for the shared ascending grid only
   if (sorted) {
     // a[j] = #{k : new_z_k < z_j}: the samples drawn from bin j (inds == j) are k in [first[j-1], first[j])
+    SNF_UNROLL_IF_CT
     for (int j = lane; j < S; j += 32) {
       const float v = zs[j];
       int lo = j >= 1 ? first[min(j - 1, nc - 1)] : 0, hi = j < nc ? first[j] : n_new;
@@ -295,7 +315,9 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
       if (k < n_new) comb[k + bk[i]] = nz[k];               // rank of new_z_k: k + #{z <= new_z_k}
     }
   } else {  // rare: an input is not monotone (rounding at a bin edge, NaN) -> odd-even transposition sort
+    SNF_UNROLL_IF_CT
     for (int j = lane; j < S; j += 32) comb[j] = zs[j];
+    SNF_UNROLL_IF_CT
     for (int k = lane; k < n_new; k += 32) comb[S + k] = nz[k];
     __syncwarp();
     for (int phase = 0; phase < T; ++phase) {
@@ -307,6 +329,7 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
     }
   }
   __syncwarp();
+  SNF_UNROLL_IF_CT
   for (int j = lane; j < T; j += 32) __stcs(z_comb + ray * T + j, comb[j]);
 }
 
@@ -353,6 +376,8 @@ int snf_sampling_set_attributes() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(hier_kernel<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHierMaxSmem)
   SNF_ATTR(1); SNF_ATTR(2); SNF_ATTR(4); SNF_ATTR(8); SNF_ATTR(16);
 #undef SNF_ATTR
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(hier_kernel<4, 64, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHierMaxSmem);
   return (int)e;
 }
 
@@ -401,6 +426,12 @@ static int hier_launch(const float *z_vals, const float *weights, const float *u
 #define SNF_LAUNCH(PER) \
   hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out, u_per_ray)
   const int per = (n_new + 31) / 32;
+  if (S == 64 && n_new == 128 && !u_per_ray) {   // the configs' shape, compile-time sized
+    hier_kernel<4, 64, 128, 0><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb,
+                                                                              inds, cdf_out, 0);
+    count_launch();
+    return launch_status();
+  }
   if (per <= 1) SNF_LAUNCH(1); else if (per <= 2) SNF_LAUNCH(2); else if (per <= 4) SNF_LAUNCH(4);
   else if (per <= 8) SNF_LAUNCH(8); else SNF_LAUNCH(16);
 #undef SNF_LAUNCH
