@@ -305,6 +305,15 @@ __device__ __forceinline__ int dt_channel(float wl) {   // wavelength value -> r
   }
 }
 
+// the same mapping without branches (lane c decodes channel c: the switch above would serialise seven paths)
+__device__ __forceinline__ int dt_channel_sel(float wl) {
+  const int w = (int)wl;
+  int k = -1;
+  k = w == 94 ? 0 : k; k = w == 131 ? 1 : k; k = w == 171 ? 2 : k; k = w == 193 ? 3 : k;
+  k = w == 211 ? 4 : k; k = w == 304 ? 5 : k; k = w == 335 ? 6 : k;
+  return k;
+}
+
 // segment lookup shared by all channels of a sample: idxl in [0,99] or -1 when theta is outside [x0, x100]
 __device__ __forceinline__ int dt_segment(const DtTables *t, float th) {
   if (!(th >= t->x[0]) || !(th <= t->x[SNF_TABLE_LEN - 1])) return -1;   // extrap=0 (also NaN)
@@ -596,8 +605,6 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
   return v;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // true when table_x is the 0.05-step grid the arithmetic segment guess assumes (within 2e-3: the guess is then off by at
 // most one segment); every thread of the CTA must call it
 __device__ __forceinline__ bool dt_grid_is_uniform(const DtTables *t) {
@@ -732,16 +739,7 @@ __global__ void __launch_bounds__(kRayWarps * 32)
       zz[c] = __ldcs(reinterpret_cast<const float2 *>(z + ray * S) + c * 32 + lane);
       v[c] = __ldcs(reinterpret_cast<const float4 *>(inf + ray * S) + c * 32 + lane);
     }
-    const int k_lane = lane < C ? dt_channel(__ldg(wavelengths + ray * C + lane)) : -1;   // lane c: table row of channel c
-    if (ray + stride < N) {   // this warp's next ray on its way into L1 while this one is computed (the kernel is issue-bound;
-                              // ncu showed 12-17 % of the samples waiting for the first load of a ray)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        prefetch_l1(reinterpret_cast<const float2 *>(z + (ray + stride) * S) + c * 32 + lane);
-        prefetch_l1(reinterpret_cast<const float4 *>(inf + (ray + stride) * S) + c * 32 + lane);
-      }
-      if (lane == 0) prefetch_l1(wavelengths + (ray + stride) * C);
-    }
+    const int k_lane = lane < C ? dt_channel_sel(__ldg(wavelengths + ray * C + lane)) : -1;   // lane c: table row of channel c
     const float nk_lane = k_lane >= 0 ? -lds_f32(kappa_s + 4 * k_lane) * 1.4426950408889634f : 0.f;  // exp(-kappa B/2) = 2^(nk B/2)
     double qsum = 0.0;
 #pragma unroll
@@ -815,17 +813,8 @@ __global__ void __launch_bounds__(kRayWarps * 32)
       v[c] = __ldcs(reinterpret_cast<const float4 *>(inf + ray * S) + c * 32 + lane);
       greg[c] = g_regq != nullptr ? __ldcs(reinterpret_cast<const float2 *>(g_regq + ray * S) + c * 32 + lane) : make_float2(0.f, 0.f);
     }
-    const int k_lane = lane < C ? dt_channel(__ldg(wavelengths + ray * C + lane)) : -1;
+    const int k_lane = lane < C ? dt_channel_sel(__ldg(wavelengths + ray * C + lane)) : -1;
     const float gi_lane = lane < C ? __ldg(g_image + ray * C + lane) : 0.f;
-    if (ray + stride < N) {   // this warp's next ray on its way into L1 while this one is computed
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        prefetch_l1(reinterpret_cast<const float2 *>(z + (ray + stride) * S) + c * 32 + lane);
-        prefetch_l1(reinterpret_cast<const float4 *>(inf + (ray + stride) * S) + c * 32 + lane);
-        if (g_regq != nullptr) prefetch_l1(reinterpret_cast<const float2 *>(g_regq + (ray + stride) * S) + c * 32 + lane);
-      }
-      if (lane == 0) { prefetch_l1(wavelengths + (ray + stride) * C); prefetch_l1(g_image + (ray + stride) * C); }
-    }
     const float kap_lane = k_lane >= 0 ? lds_f32(kappa_s + 4 * k_lane) : 0.f;
     DtPairRay<NC> r;
     dt_pair_setup<NC>(r, tab, x_s, ys_s, uniform, zz, v, lane);

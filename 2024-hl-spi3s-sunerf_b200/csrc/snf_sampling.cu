@@ -262,9 +262,11 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
   __syncwarp();
   SNF_UNROLL_IF_CT
   for (int i = lane; i < ncnt; i += 32) cnt[i] = 0;         // reused for the merge below
+  float nzr[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int k = lane * PER + i;
+    nzr[i] = 0.f;
     if (k < n_new) {
       const float uu = us[k];
       const int lo = ind[i];
@@ -275,19 +277,27 @@ __global__ void __launch_bounds__(128) hier_kernel(const float *__restrict__ z_v
       const float t = fdiv(fsub(uu, cb), denom);                                     // :166
       const float s = fadd(bb, fmul(t, fsub(ba, bb)));                               // :167
       nz[k] = s;
+      nzr[i] = s;
       if (inds != nullptr) inds[ray * n_new + k] = lo;
     }
   }
   __syncwarp();
-  SNF_UNROLL_IF_CT
-  for (int k = lane; k < n_new; k += 32) __stcs(new_z + ray * n_new + k, nz[k]);     // coalesced copy of the row
+  bool sorted = true;
+  if constexpr (NC > 0 && PER == 4) {
+    // the lane's four consecutive samples leave as one 16-byte store and are checked for order in registers
+    __stcs(reinterpret_cast<float4 *>(new_z + ray * n_new) + lane, make_float4(nzr[0], nzr[1], nzr[2], nzr[3]));
+    const float nxt = __shfl_down_sync(kFull, nzr[0], 1);
+    sorted = (nzr[0] <= nzr[1]) & (nzr[1] <= nzr[2]) & (nzr[2] <= nzr[3]) & (lane == 31 || nzr[3] <= nxt);
+  } else {
+    SNF_UNROLL_IF_CT
+    for (int k = lane; k < n_new; k += 32) __stcs(new_z + ray * n_new + k, nz[k]);   // coalesced copy of the row
+    SNF_UNROLL_IF_CT
+    for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
+  }
 
   // ---- sort(cat(z, new_z))  :123
-  bool sorted = true;
   SNF_UNROLL_IF_CT
   for (int j = lane; j < S - 1; j += 32) sorted &= (zs[j] <= zs[j + 1]);
-  SNF_UNROLL_IF_CT
-  for (int k = lane; k < n_new - 1; k += 32) sorted &= (nz[k] <= nz[k + 1]);
   sorted = __all_sync(kFull, sorted) && !u_per_ray;        // first[] exists for the shared ascending grid only
   if (sorted) {
     // a[j] = #{k : new_z_k < z_j}: the samples drawn from bin j (inds == j) are k in [first[j-1], first[j])
@@ -426,7 +436,7 @@ static int hier_launch(const float *z_vals, const float *weights, const float *u
 #define SNF_LAUNCH(PER) \
   hier_kernel<PER><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb, inds, cdf_out, u_per_ray)
   const int per = (n_new + 31) / 32;
-  if (S == 64 && n_new == 128 && !u_per_ray) {   // the configs' shape, compile-time sized
+  if (S == 64 && n_new == 128 && !u_per_ray && (reinterpret_cast<uintptr_t>(new_z) & 15) == 0) {   // the configs' shape, compile-time sized
     hier_kernel<4, 64, 128, 0><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, N, S, n_new, new_z, z_comb,
                                                                               inds, cdf_out, 0);
     count_launch();
