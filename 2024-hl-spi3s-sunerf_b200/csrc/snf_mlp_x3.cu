@@ -120,6 +120,16 @@ __device__ __forceinline__ uint32_t cosq_enc_full(float c) {
   return c < 0.f ? (q | 0x80u) : q;
 }
 
+// chunks c8, c8 + 1 (c8 even; v[0..3], v[4..7]) of row `row` of a SWIZZLE_128B slab as ONE 32-byte store
+__device__ __forceinline__ void st_row_pair(uint8_t *slab, int row, int c8, const uint32_t *v) {
+  const bool odd = row & 1;                       // (c8 ^ r) and (c8 + 1) ^ r share the aligned pair; odd rows swap them
+  uint8_t *dst = slab + (row >> 3) * 1024 + (row & 7) * 128 + (((c8 ^ (row & 7)) & ~1) << 4);
+  const uint32_t a0 = odd ? v[4] : v[0], a1 = odd ? v[5] : v[1], a2 = odd ? v[6] : v[2], a3 = odd ? v[7] : v[3];
+  const uint32_t b0 = odd ? v[0] : v[4], b1 = odd ? v[1] : v[5], b2 = odd ? v[2] : v[6], b3 = odd ? v[3] : v[7];
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0),
+               "r"(b1), "r"(b2), "r"(b3) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_x3_layer_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -265,17 +275,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_x3_l
             o1 += sv[0] * wb.x + sv[1] * wb.y + sv[2] * wb.z + sv[3] * wb.w;
           }
         }
+        // Each lane owns a ROW of the tile image (rows are 128 B apart), so a warp store touches 32 lines whatever its
+        // width: the kernel was bound by these L1 wavefronts (8192 per item in rendering against 12288 MMA cycles - the 67 %
+        // tensor-pipe activity ncu showed).  sm_100 has 256-bit stores: the 128-byte swizzle XORs the chunk index with
+        // row mod 8, which keeps an aligned PAIR of 16-byte chunks together (swapped in odd rows) - half the instructions.
         if (ohi != nullptr) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4 *>(ohi + slab * SLAB_BYTES + sw128_chunk_off(row, c8_0 + k)) =
-                make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+          for (int k = 0; k < 4; k += 2) st_row_pair(ohi + slab * SLAB_BYTES, row, c8_0 + k, &hi[4 * k]);
         }
         if (olo != nullptr) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4 *>(olo + slab * SLAB_BYTES + sw128_chunk_off(row, c8_0 + k)) =
-                make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+          for (int k = 0; k < 4; k += 2) st_row_pair(olo + slab * SLAB_BYTES, row, c8_0 + k, &lo[4 * k]);
         }
         if (cod != nullptr) {
           const int ch16 = (ncol & 63) >> 4;
