@@ -196,9 +196,12 @@ class RayTrainer:
         same optimiser step as everybody else, so the replicas stay identical and nobody hangs in NCCL."""
         self.flat_grad.zero_()
         # the SAME issue order as _step_impl on the ranks that have rays (collectives pair up by order, and the two buckets
-        # have the same size: a swapped order would silently add fine gradients to coarse ones)
-        order = ('coarse_model', 'fine_model') if self.early_coarse_reduce else ('fine_model', 'coarse_model')
-        parallel.wait_all([self._reduce_async(name) for name in order])
+        # have the same size: a swapped order would silently add fine gradients to coarse ones;
+        # the late schedule exchanges the whole flat gradient in one call)
+        if self.early_coarse_reduce:
+            parallel.wait_all([self._reduce_async('coarse_model'), self._reduce_async('fine_model')])
+        else:
+            parallel.wait_all([parallel.allreduce_sum_async(self.flat_grad, 0, self.n_flat, self.pg)])
         self._optimizer_step(self._device_sched)
         self._host_bookkeeping()
         nan = torch.full((4,), float('nan'), device=self.dev)
@@ -290,11 +293,16 @@ class RayTrainer:
         else:
             g_raw_f = ops.composite_emission_bwd(raw_f, z_comb, rays_d, g_if.view(-1), g_q)
         ops.mlp_backward(q_f.view(-1, 4), w_f, g_raw_f.view(-1, 2), ws_f, gw_f, gb_f, packed_ptr=pk_f)
-        h_fine = self._reduce_async('fine_model')
-        if side is not main:
-            main.wait_stream(side)
-        if not self.early_coarse_reduce:
-            h_coarse = self._reduce_async('coarse_model')
+        if self.early_coarse_reduce:
+            h_fine = self._reduce_async('fine_model')
+            if side is not main:
+                main.wait_stream(side)
+        else:
+            # late schedule: both buckets are complete here and contiguous - ONE all-reduce of the whole flat gradient
+            # (15 MB on NVSwitch is latency-bound: a second NCCL launch costs more than its bytes)
+            if side is not main:
+                main.wait_stream(side)
+            h_fine, h_coarse = parallel.allreduce_sum_async(self.flat_grad, 0, self.n_flat, self.pg), None
         parallel.wait_all([h_coarse, h_fine])
         # ---- optimiser
         self._optimizer_step(device_sched)
