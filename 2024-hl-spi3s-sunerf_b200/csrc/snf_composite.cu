@@ -576,9 +576,9 @@ __global__ void __launch_bounds__(kRayWarps * 32)
 }
 
 // ------------------------------------------------------------------------------------------------ K6, S = 64 NC
-// The pair layout of K5 (lane l owns samples 64 c + 2 l, 64 c + 2 l + 1 of chunk c) for the density-temperature head.  The
-// kernel is bound by instruction issue (ncu: 2100 warp instructions per ray in the first pair version, the ready warps
-// "not selected"), so this version is about instructions:
+// The fast path of the density-temperature head for the configs' sample counts.  The kernel is bound by instruction issue
+// (ncu: 2100 warp instructions per ray in the first version of this path, the ready warps "not selected"), so it is about
+// instructions:
 //   * per ray, not per channel: lane c loads and decodes wavelength c (and dL/dI_c) with the ray, the channel loop gets its
 //     table row and kappa by shuffle - no dependent global load and no 25-instruction decode per channel;
 //   * everything that does not depend on the channel is folded into per-sample factors once per ray,
@@ -615,12 +615,6 @@ __device__ __forceinline__ bool dt_grid_is_uniform(const DtTables *t) {
 
 constexpr uint32_t kYsRow = (SNF_TABLE_LEN - 1) * sizeof(float2);   // bytes between the (y, slope) rows of two channels
 
-template <int NC>
-struct DtPairRay {
-  float rho[2 * NC], dxq[2 * NC], dzn[2 * NC], dzp[2 * NC], Bh[2 * NC], wr[2 * NC];
-  uint32_t ysa[2 * NC];   // shared address of the sample's segment in channel 0's (y, slope) row (segment 0 when outside)
-};
-
 // segment of th: x[g] < th <= x[g+1] (searchsorted left, clamped), -1 outside the table; x_s = shared address of tab->x
 __device__ __forceinline__ int dt_segment_fast(const DtTables *tab, uint32_t x_s, float x0, float xN, float th, bool uniform,
                                                float &xg) {
@@ -638,56 +632,77 @@ __device__ __forceinline__ int dt_segment_fast(const DtTables *tab, uint32_t x_s
   return (th >= x0 && th <= xN) ? g : -1;             // extrap = 0 (also NaN)
 }
 
-template <int NC>
-__device__ __forceinline__ void dt_pair_setup(DtPairRay<NC> &r, const DtTables *tab, uint32_t x_s, uint32_t ys_s, bool uniform,
-                                              const float2 (&zz)[NC], const float4 (&v)[NC], int lane) {
+// BLOCKED layout of the fast path (S = 32 PER, PER even): lane l owns the PER consecutive samples l PER .. l PER + PER - 1, so
+// the whole ray needs ONE double-precision scan (of the lanes' totals; the prefix inside a lane is PER register adds) and one
+// neighbour exchange - the pair layout of K5 needed one per 64 samples, and with a single channel the per-ray set-up alone
+// held this kernel at 55 % of the HBM peak.  The lane's 4 PER / 8 PER contiguous bytes are read with 8 / 16-byte loads at a
+// 4 PER-byte lane stride: three times the L1 wavefronts of a dense access, the same DRAM sectors - the kernel is bound by
+// instruction issue, not by L1.
+template <int PER>
+struct DtBlkRay {
+  float rho[PER], dxq[PER], dzn[PER], dzp[PER], Bh[PER], wr[PER];
+  uint32_t ysa[PER];   // shared address of the sample's segment in channel 0's (y, slope) row (segment 0 when outside)
+};
+
+template <int PER> __device__ __forceinline__ void ld_blk(const float *row, int lane, float (&v)[PER]) {
+#pragma unroll
+  for (int i = 0; i < PER / 2; ++i) {
+    const float2 t = __ldcs(reinterpret_cast<const float2 *>(row) + lane * (PER / 2) + i);
+    v[2 * i] = t.x; v[2 * i + 1] = t.y;
+  }
+}
+template <int PER> __device__ __forceinline__ void ld_blk2(const float2 *row, int lane, float2 (&v)[PER]) {
+#pragma unroll
+  for (int i = 0; i < PER / 2; ++i) {
+    const float4 t = __ldcs(reinterpret_cast<const float4 *>(row) + lane * (PER / 2) + i);
+    v[2 * i] = make_float2(t.x, t.y); v[2 * i + 1] = make_float2(t.z, t.w);
+  }
+}
+template <int PER> __device__ __forceinline__ void st_blk(float *row, int lane, const float (&v)[PER]) {
+#pragma unroll
+  for (int i = 0; i < PER / 2; ++i) __stcs(reinterpret_cast<float2 *>(row) + lane * (PER / 2) + i, make_float2(v[2 * i], v[2 * i + 1]));
+}
+
+template <int PER>
+__device__ __forceinline__ void dt_blk_setup(DtBlkRay<PER> &r, const DtTables *tab, uint32_t x_s, uint32_t ys_s, bool uniform,
+                                             const float (&z)[PER], const float2 (&v)[PER], int lane) {
   const float x0 = lds_f32(x_s), xN = lds_f32(x_s + 4 * (SNF_TABLE_LEN - 1));
-  bool in[2 * NC];
+  bool in[PER];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int e = 2 * c + h;
-      r.rho[e] = expf(fmaxf(h ? v[c].z : v[c].x, 0.f));                       // :237
-      const float th = fmaxf(h ? v[c].w : v[c].y, 0.f);                       // :241
-      float xg;
-      const int sg = dt_segment_fast(tab, x_s, x0, xN, th, uniform, xg);
-      in[e] = sg >= 0;
-      r.ysa[e] = ys_s + (uint32_t)(sg >= 0 ? sg : 0) * (uint32_t)sizeof(float2);
-      r.dxq[e] = sg >= 0 ? fsub(th, xg) : 0.f;
-    }
+  for (int i = 0; i < PER; ++i) {
+    r.rho[i] = expf(fmaxf(v[i].x, 0.f));                                      // :237
+    const float th = fmaxf(v[i].y, 0.f);                                      // :241
+    float xg;
+    const int sg = dt_segment_fast(tab, x_s, x0, xN, th, uniform, xg);
+    in[i] = sg >= 0;
+    r.ysa[i] = ys_s + (uint32_t)(sg >= 0 ? sg : 0) * (uint32_t)sizeof(float2);
+    r.dxq[i] = sg >= 0 ? fsub(th, xg) : 0.f;
   }
-  double carry = 0.0;
+  // term_k = dz_k (rho_k + rho_{k+1}), B = inclusive cumulative sum (:261, x 2); the last sample of the ray has no successor
+  const float zdn = __shfl_down_sync(kFull, z[0], 1), rdn = __shfl_down_sync(kFull, r.rho[0], 1);
+  double pre[PER];
+  double run = 0.0;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    // next sample of the pair's second element: lane + 1's first element, or the next chunk's lane 0
-    const float zdn = __shfl_down_sync(kFull, zz[c].x, 1), rdn = __shfl_down_sync(kFull, r.rho[2 * c], 1);
-    const float zfn = __shfl_sync(kFull, zz[c + 1 < NC ? c + 1 : c].x, 0), rfn = __shfl_sync(kFull, r.rho[2 * (c + 1 < NC ? c + 1 : c)], 0);
-    const bool last = (c == NC - 1) && lane == 31;                            // sample S - 1 has no successor
-    const float zn1 = lane < 31 ? zdn : zfn, rn1 = lane < 31 ? rdn : rfn;
-    const float dz0 = fsub(zz[c].y, zz[c].x), dz1 = last ? 0.f : fsub(zn1, zz[c].y);
-    const double t0 = (double)fmul(dz0, fadd(r.rho[2 * c], r.rho[2 * c + 1]));
-    const double t1 = last ? 0.0 : (double)fmul(dz1, fadd(r.rho[2 * c + 1], rn1));
-    const double incl = warp_incl_sum(t0 + t1, lane);
-    double excl = shfl_up_d(incl, 1);
-    if (lane == 0) excl = 0.0;
-    const double B0 = carry + excl + t0, B1 = B0 + t1;                        // inclusive cumulative sums (:261, x 2)
-    r.dzn[2 * c] = dz0; r.dzn[2 * c + 1] = dz1;
-    r.Bh[2 * c] = 0.5f * (float)B0; r.Bh[2 * c + 1] = 0.5f * (float)B1;
-    carry += __shfl_sync(kFull, incl, 31);
+  for (int i = 0; i < PER; ++i) {
+    const bool last = (i == PER - 1) && lane == 31;
+    const float zn = i + 1 < PER ? z[i + 1 < PER ? i + 1 : i] : zdn, rn = i + 1 < PER ? r.rho[i + 1 < PER ? i + 1 : i] : rdn;
+    r.dzn[i] = last ? 0.f : fsub(zn, z[i]);
+    run += last ? 0.0 : (double)fmul(r.dzn[i], fadd(r.rho[i], rn));
+    pre[i] = run;
   }
+  const double incl = warp_incl_sum(run, lane);
+  double excl = shfl_up_d(incl, 1);
+  if (lane == 0) excl = 0.0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) r.Bh[i] = 0.5f * (float)(excl + pre[i]);
   // trapezoid node weights over z[0..S-2]: w_k = (dz_{k-1} [k >= 1] + dz_k [k <= S-3]) / 2, 0 at k = S - 1
+  const float up = __shfl_up_sync(kFull, r.dzn[PER - 1], 1);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const float up = __shfl_up_sync(kFull, r.dzn[2 * c + 1], 1);
-    const float pl = __shfl_sync(kFull, r.dzn[2 * (c > 0 ? c - 1 : 0) + 1], 31);
-    const float dzp0 = lane > 0 ? up : (c > 0 ? pl : 0.f);                    // 0 at sample 0
-    const bool l31 = (c == NC - 1) && lane == 31;                             // holds samples S - 2 and S - 1
-    r.dzp[2 * c] = dzp0; r.dzp[2 * c + 1] = r.dzn[2 * c];
-    const float wk0 = 0.5f * (dzp0 + (l31 ? 0.f : r.dzn[2 * c]));
-    const float wk1 = l31 ? 0.f : 0.5f * (r.dzn[2 * c] + r.dzn[2 * c + 1]);
-    r.wr[2 * c] = in[2 * c] ? wk0 * fmul(r.rho[2 * c], r.rho[2 * c]) : 0.f;              // :263
-    r.wr[2 * c + 1] = in[2 * c + 1] ? wk1 * fmul(r.rho[2 * c + 1], r.rho[2 * c + 1]) : 0.f;
+  for (int i = 0; i < PER; ++i) {
+    r.dzp[i] = i > 0 ? r.dzn[i > 0 ? i - 1 : 0] : (lane > 0 ? up : 0.f);      // 0 at sample 0
+    const bool s1 = lane == 31 && i == PER - 1, s2 = lane == 31 && i == PER - 2;   // samples S - 1, S - 2
+    const float wk = s1 ? 0.f : 0.5f * (r.dzp[i] + (s2 ? 0.f : r.dzn[i]));
+    r.wr[i] = in[i] ? wk * fmul(r.rho[i], r.rho[i]) : 0.f;                    // :263
   }
 }
 
@@ -713,14 +728,14 @@ __device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
   return t;
 }
 
-template <int NC>
+template <int PER>
 __global__ void __launch_bounds__(kRayWarps * 32)
-    composite_dt_fwd_pair_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
-                                 const float *__restrict__ wavelengths, int64_t N, int C,
-                                 const float *__restrict__ log_abs, const float *__restrict__ vol_c,
-                                 const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
-                                 float *__restrict__ image, float *__restrict__ weights, float *__restrict__ regq) {
-  constexpr int S = 64 * NC;
+    composite_dt_fwd_blk_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
+                                const float *__restrict__ wavelengths, int64_t N, int C,
+                                const float *__restrict__ log_abs, const float *__restrict__ vol_c,
+                                const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
+                                float *__restrict__ image, float *__restrict__ weights, float *__restrict__ regq) {
+  constexpr int S = 32 * PER;
   __shared__ DtTables tabs;
   const DtTables *tab = &tabs;
   dt_load_tables(&tabs, table_x, table_y, log_abs);
@@ -732,29 +747,23 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   const float vc = vol_c[0];
   const int64_t stride = (int64_t)gridDim.x * kRayWarps;
   for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += stride) {
-    float2 zz[NC];
-    float4 v[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      zz[c] = __ldcs(reinterpret_cast<const float2 *>(z + ray * S) + c * 32 + lane);
-      v[c] = __ldcs(reinterpret_cast<const float4 *>(inf + ray * S) + c * 32 + lane);
-    }
+    float zz[PER];
+    float2 v[PER];
+    ld_blk<PER>(z + ray * S, lane, zz);
+    ld_blk2<PER>(inf + ray * S, lane, v);
     const int k_lane = lane < C ? dt_channel_sel(__ldg(wavelengths + ray * C + lane)) : -1;   // lane c: table row of channel c
     const float nk_lane = k_lane >= 0 ? -lds_f32(kappa_s + 4 * k_lane) * 1.4426950408889634f : 0.f;  // exp(-kappa B/2) = 2^(nk B/2)
+    float q[PER];
     double qsum = 0.0;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float q0 = fmaxf(v[c].x, 0.f), q1 = fmaxf(v[c].z, 0.f);
-      __stcs(reinterpret_cast<float2 *>(regq + ray * S) + c * 32 + lane, make_float2(q0, q1));   // :271
-      qsum += (double)q0 + (double)q1;
-    }
+    for (int i = 0; i < PER; ++i) { q[i] = fmaxf(v[i].x, 0.f); qsum += (double)q[i]; }
+    st_blk<PER>(regq + ray * S, lane, q);                                                       // :271
     const float den = fadd((float)warp_sum(qsum), 1e-10f);
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
-      __stcs(reinterpret_cast<float2 *>(weights + ray * S) + c * 32 + lane,
-             make_float2(fdiv(fmaxf(v[c].x, 0.f), den), fdiv(fmaxf(v[c].z, 0.f), den)));         // :268-269
-    DtPairRay<NC> r;
-    dt_pair_setup<NC>(r, tab, x_s, ys_s, uniform, zz, v, lane);
+    for (int i = 0; i < PER; ++i) q[i] = fdiv(q[i], den);                                       // :268-269
+    st_blk<PER>(weights + ray * S, lane, q);
+    DtBlkRay<PER> r;
+    dt_blk_setup<PER>(r, tab, x_s, ys_s, uniform, zz, v, lane);
     float part[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -766,7 +775,7 @@ __global__ void __launch_bounds__(kRayWarps * 32)
           const uint32_t koff = (uint32_t)k * kYsRow;
           float acc = 0.f;
 #pragma unroll
-          for (int e = 0; e < 2 * NC; ++e) {
+          for (int e = 0; e < PER; ++e) {
             const float2 ys = lds_f32x2(r.ysa[e] + koff);
             const float R = fmaf(r.dxq[e], ys.y, ys.x);                         // :248 linear interpolation
             acc = fmaf(r.wr[e], ex2_ftz(nk * r.Bh[e]) * R, acc);                // :264-265
@@ -781,15 +790,15 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   }
 }
 
-template <int NC>
+template <int PER>
 __global__ void __launch_bounds__(kRayWarps * 32)
-    composite_dt_bwd_pair_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
-                                 const float *__restrict__ wavelengths, int64_t N, int C,
-                                 const float *__restrict__ log_abs, const float *__restrict__ vol_c,
-                                 const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
-                                 const float *__restrict__ g_image, const float *__restrict__ g_regq,
-                                 float2 *__restrict__ g_inf, float *__restrict__ g_log_abs, float *__restrict__ g_vol_c) {
-  constexpr int S = 64 * NC;
+    composite_dt_bwd_blk_kernel(const float2 *__restrict__ inf, const float *__restrict__ z,
+                                const float *__restrict__ wavelengths, int64_t N, int C,
+                                const float *__restrict__ log_abs, const float *__restrict__ vol_c,
+                                const float *__restrict__ table_x, const float *__restrict__ table_y, float F,
+                                const float *__restrict__ g_image, const float *__restrict__ g_regq,
+                                float2 *__restrict__ g_inf, float *__restrict__ g_log_abs, float *__restrict__ g_vol_c) {
+  constexpr int S = 32 * PER;
   __shared__ DtTables tabs;
   __shared__ float blk_acc[8];   // 7 kappa grads + vol_c grad of this CTA's rays
   const DtTables *tab = &tabs;
@@ -805,23 +814,25 @@ __global__ void __launch_bounds__(kRayWarps * 32)
   float gvc = 0.f;               // per-lane partial of dL/dvol_c, reduced once at the end
   const int64_t stride = (int64_t)gridDim.x * kRayWarps;
   for (int64_t ray = (int64_t)blockIdx.x * kRayWarps + warp; ray < N; ray += stride) {
-    float2 zz[NC], greg[NC];
-    float4 v[NC];
+    float zz[PER], greg[PER];
+    float2 v[PER];
+    ld_blk<PER>(z + ray * S, lane, zz);
+    ld_blk2<PER>(inf + ray * S, lane, v);
+    if (g_regq != nullptr) {
+      ld_blk<PER>(g_regq + ray * S, lane, greg);
+    } else {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      zz[c] = __ldcs(reinterpret_cast<const float2 *>(z + ray * S) + c * 32 + lane);
-      v[c] = __ldcs(reinterpret_cast<const float4 *>(inf + ray * S) + c * 32 + lane);
-      greg[c] = g_regq != nullptr ? __ldcs(reinterpret_cast<const float2 *>(g_regq + ray * S) + c * 32 + lane) : make_float2(0.f, 0.f);
+      for (int i = 0; i < PER; ++i) greg[i] = 0.f;
     }
     const int k_lane = lane < C ? dt_channel_sel(__ldg(wavelengths + ray * C + lane)) : -1;
     const float gi_lane = lane < C ? __ldg(g_image + ray * C + lane) : 0.f;
     const float kap_lane = k_lane >= 0 ? lds_f32(kappa_s + 4 * k_lane) : 0.f;
-    DtPairRay<NC> r;
-    dt_pair_setup<NC>(r, tab, x_s, ys_s, uniform, zz, v, lane);
+    DtBlkRay<PER> r;
+    dt_blk_setup<PER>(r, tab, x_s, ys_s, uniform, zz, v, lane);
     // per sample, summed over the channels: s1 = sum_c Gc u_c (u = w tau), dth = dL/dtheta, dB = dL/dB
-    float s1[2 * NC], dth[2 * NC], dB[2 * NC], dkc[8];
+    float s1[PER], dth[PER], dB[PER], dkc[8];
 #pragma unroll
-    for (int e = 0; e < 2 * NC; ++e) s1[e] = dth[e] = dB[e] = 0.f;
+    for (int e = 0; e < PER; ++e) s1[e] = dth[e] = dB[e] = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       dkc[c] = 0.f;
@@ -835,7 +846,7 @@ __global__ void __launch_bounds__(kRayWarps * 32)
           const uint32_t koff = (uint32_t)k * kYsRow;
           float part = 0.f, dk = 0.f;
 #pragma unroll
-          for (int e = 0; e < 2 * NC; ++e) {
+          for (int e = 0; e < PER; ++e) {
             const float2 ys = lds_f32x2(r.ysa[e] + koff);
             const float R = fmaf(r.dxq[e], ys.y, ys.x);
             const float eA = ex2_ftz(nk * r.Bh[e]);
@@ -858,37 +869,34 @@ __global__ void __launch_bounds__(kRayWarps * 32)
       const int k = __shfl_sync(kFull, k_lane, ch);
       if ((lane & 3) == 0 && k >= 0 && t != 0.f && lds_f32(kon_s + 4 * k) != 0.f) atomicAdd(&blk_acc[k], t);
     }
-    // G_i = sum_{k>=i} dL/dB_k = dL/d term_i, term_i = dz_i (rho_i + rho_{i+1}): one suffix scan per chunk for all channels
-    float G[2 * NC];
-    float rcarry = 0.f;
+    // G_i = sum_{k>=i} dL/dB_k = dL/d term_i, term_i = dz_i (rho_i + rho_{i+1}): suffix sums inside the lane, one suffix scan
+    // of the lanes' totals for all channels
+    float G[PER];
+    float run = 0.f;
 #pragma unroll
-    for (int c = NC - 1; c >= 0; --c) {
-      float suf = dB[2 * c] + dB[2 * c + 1];
+    for (int i = PER - 1; i >= 0; --i) { run += dB[i]; G[i] = run; }
+    float suf = run;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float n = __shfl_down_sync(kFull, suf, d);
-        if (lane + d < 32) suf += n;
-      }
-      suf += rcarry;
-      G[2 * c] = suf;                          // inclusive suffix at the pair's first sample
-      G[2 * c + 1] = suf - dB[2 * c];
-      rcarry = __shfl_sync(kFull, suf, 0);
+    for (int d = 1; d < 32; d <<= 1) {
+      const float n = __shfl_down_sync(kFull, suf, d);
+      if (lane + d < 32) suf += n;
+    }
+    const float later = suf - run;                 // lanes above this one
+#pragma unroll
+    for (int i = 0; i < PER; ++i) G[i] += later;
+    const float gup = __shfl_up_sync(kFull, G[PER - 1], 1);
+    float2 o[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float Gp = i > 0 ? G[i > 0 ? i - 1 : 0] : (lane > 0 ? gup : 0.f);   // G of the previous sample (none at sample 0: dzp = 0)
+      // d term_i / d rho_j: dz_j for i = j (dzn is 0 at S-1) and dz_{j-1} for i = j - 1
+      const float dr = s1[i] * (2.f / r.rho[i]) + r.dzn[i] * G[i] + r.dzp[i] * Gp;
+      o[i].x = v[i].x > 0.f ? dr * r.rho[i] + greg[i] : 0.f;
+      o[i].y = v[i].y > 0.f ? dth[i] : 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float gup = __shfl_up_sync(kFull, G[2 * c + 1], 1);
-      const float gpl = __shfl_sync(kFull, G[2 * (c > 0 ? c - 1 : 0) + 1], 31);
-      const float Gp0 = lane > 0 ? gup : (c > 0 ? gpl : 0.f);                 // G of the previous sample (none at sample 0: dzp = 0)
-      // d term_i / d rho_j: dz_j for i = j (j <= S-2: dzn is 0 at S-1) and dz_{j-1} for i = j - 1
-      const float dr0 = s1[2 * c] * (2.f / r.rho[2 * c]) + r.dzn[2 * c] * G[2 * c] + r.dzp[2 * c] * Gp0;
-      const float dr1 = s1[2 * c + 1] * (2.f / r.rho[2 * c + 1]) + r.dzn[2 * c + 1] * G[2 * c + 1] + r.dzp[2 * c + 1] * G[2 * c];
-      float4 o;
-      o.x = v[c].x > 0.f ? dr0 * r.rho[2 * c] + greg[c].x : 0.f;
-      o.y = v[c].y > 0.f ? dth[2 * c] : 0.f;
-      o.z = v[c].z > 0.f ? dr1 * r.rho[2 * c + 1] + greg[c].y : 0.f;
-      o.w = v[c].w > 0.f ? dth[2 * c + 1] : 0.f;
-      __stcs(reinterpret_cast<float4 *>(g_inf + ray * S) + c * 32 + lane, o);
-    }
+    for (int i = 0; i < PER / 2; ++i)
+      __stcs(reinterpret_cast<float4 *>(g_inf + ray * S) + lane * (PER / 2) + i, make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y));
   }
   gvc = warp_sum_f(gvc);
   if (lane == 0 && gvc != 0.f) atomicAdd(&blk_acc[7], gvc);
@@ -1083,10 +1091,10 @@ extern "C" int snf_composite_dt_fwd(const float *inferences, const float *z, con
   const float2 *inf2 = reinterpret_cast<const float2 *>(inferences);
   if (S % 64 == 0 && ((reinterpret_cast<uintptr_t>(inferences) & 15) | (reinterpret_cast<uintptr_t>(z) & 7) |
                       (reinterpret_cast<uintptr_t>(weights) & 7) | (reinterpret_cast<uintptr_t>(regq) & 7)) == 0) {
-#define SNF_LAUNCH_P(NC) \
-  composite_dt_fwd_pair_kernel<NC><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
+#define SNF_LAUNCH_P(PER) \
+  composite_dt_fwd_blk_kernel<PER><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
       inf2, z, wavelengths, N, C, log_abs, vol_c, table_x, table_y, F, image, weights, regq)
-    switch (S / 64) { case 1: SNF_LAUNCH_P(1); break; case 2: SNF_LAUNCH_P(2); break; case 3: SNF_LAUNCH_P(3); break; default: SNF_LAUNCH_P(4); break; }
+    switch (S / 64) { case 1: SNF_LAUNCH_P(2); break; case 2: SNF_LAUNCH_P(4); break; case 3: SNF_LAUNCH_P(6); break; default: SNF_LAUNCH_P(8); break; }
 #undef SNF_LAUNCH_P
     count_launch();
     return launch_status();
@@ -1120,10 +1128,10 @@ extern "C" int snf_composite_dt_bwd(const float *inferences, const float *z, con
   float2 *g2 = reinterpret_cast<float2 *>(g_inferences);
   if (S % 64 == 0 && ((reinterpret_cast<uintptr_t>(inferences) & 15) | (reinterpret_cast<uintptr_t>(z) & 7) |
                       (reinterpret_cast<uintptr_t>(g_inferences) & 15) | (reinterpret_cast<uintptr_t>(g_regq) & 7)) == 0) {
-#define SNF_LAUNCH_P(NC) \
-  composite_dt_bwd_pair_kernel<NC><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
+#define SNF_LAUNCH_P(PER) \
+  composite_dt_bwd_blk_kernel<PER><<<(unsigned)nblk, kRayWarps * 32, 0, (cudaStream_t)stream>>>( \
       inf2, z, wavelengths, N, C, log_abs, vol_c, table_x, table_y, F, g_image, g_regq, g2, g_log_abs, g_vol_c)
-    switch (S / 64) { case 1: SNF_LAUNCH_P(1); break; case 2: SNF_LAUNCH_P(2); break; case 3: SNF_LAUNCH_P(3); break; default: SNF_LAUNCH_P(4); break; }
+    switch (S / 64) { case 1: SNF_LAUNCH_P(2); break; case 2: SNF_LAUNCH_P(4); break; case 3: SNF_LAUNCH_P(6); break; default: SNF_LAUNCH_P(8); break; }
 #undef SNF_LAUNCH_P
     count_launch();
     return launch_status();

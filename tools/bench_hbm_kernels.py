@@ -14,6 +14,7 @@ ap.add_argument('--rays', type=int, default=1 << 20)
 ap.add_argument('--iters', type=int, default=10)
 ap.add_argument('--json', default=None)
 ap.add_argument('--only', default=None)
+ap.add_argument('--dt-channels', default='7', help='comma-separated channel counts for the K6 rows (default: 7, DT_2012_11.yaml)')
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
 N = args.rays
@@ -82,8 +83,10 @@ if want('dt'):
     la = torch.full((7,), 1e-6, device=dev)
     vc = torch.ones(1, device=dev)
     tx, ty = rend._table_x, rend._table_y
-    rows.append(timeit(lambda: ops.composite_dt_fwd(inf, zz, wl, la, vc, tx, ty, 1e17), Nd * (20 * 192 + 8 * 7), 'K6 composite_dt_fwd (S=192, C=7)'))
-    gi = torch.randn(Nd, 7, device=dev, generator=g)
-    rows.append(timeit(lambda: ops.composite_dt_bwd(inf, zz, wl, la, vc, tx, ty, 1e17, gi), Nd * (28 * 192 + 8 * 7), 'K6 composite_dt_bwd (S=192, C=7)'))
+    for C in [int(c) for c in args.dt_channels.split(',')]:
+        wlc = wl[:, :C].contiguous()
+        rows.append(timeit(lambda: ops.composite_dt_fwd(inf, zz, wlc, la, vc, tx, ty, 1e17), Nd * (20 * 192 + 8 * C), f'K6 composite_dt_fwd (S=192, C={C})'))
+        gi = torch.randn(Nd, C, device=dev, generator=g)
+        rows.append(timeit(lambda: ops.composite_dt_bwd(inf, zz, wlc, la, vc, tx, ty, 1e17, gi), Nd * (28 * 192 + 8 * C), f'K6 composite_dt_bwd (S=192, C={C})'))
 if args.json:
     json.dump(rows, open(args.json, 'w'), indent=1)
