@@ -7,6 +7,7 @@
 //   simple_star_kernel               : sunerf/model/stellar_model.py:53-102
 //   loss kernels                     : sunerf/model/sunerf.py:98-131, 173-206; sunerf/train/scaling.py:17-28
 #include "snf_common.cuh"
+#include <type_traits>
 
 namespace snf {
 
@@ -614,6 +615,11 @@ __device__ __forceinline__ bool dt_grid_is_uniform(const DtTables *t) {
 }
 
 constexpr uint32_t kYsRow = (SNF_TABLE_LEN - 1) * sizeof(float2);   // bytes between the (y, slope) rows of two channels
+template <uint32_t IMM> __device__ __forceinline__ float2 lds_f32x2_imm(uint32_t addr) {   // [addr + IMM]: the offset rides in the instruction
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM));
+  return v;
+}
 
 // segment of th: x[g] < th <= x[g+1] (searchsorted left, clamped), -1 outside the table; x_s = shared address of tab->x
 __device__ __forceinline__ int dt_segment_fast(const DtTables *tab, uint32_t x_s, float x0, float xN, float th, bool uniform,
@@ -766,22 +772,46 @@ __global__ void __launch_bounds__(kRayWarps * 32)
     dt_blk_setup<PER>(r, tab, x_s, ys_s, uniform, zz, v, lane);
     float part[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      part[c] = 0.f;
-      if (c < C) {
-        const int k = __shfl_sync(kFull, k_lane, c);
-        const float nk = __shfl_sync(kFull, nk_lane, c);
-        if (k >= 0) {   // an absent channel keeps response and absorption 0 (:243, :251): the pixel is 0 * vol_c * F
-          const uint32_t koff = (uint32_t)k * kYsRow;
-          float acc = 0.f;
+    for (int c = 0; c < 8; ++c) part[c] = 0.f;
+    // Channels in table order (wavelength c is row c of the response table wherever it is present - every shipped config
+    // lists them that way, the STEREO mask only blanks entries): the row offset is a compile-time immediate of the load.
+    const unsigned present = __ballot_sync(kFull, k_lane >= 0);
+    const bool in_order = __all_sync(kFull, k_lane < 0 || k_lane == lane);
+    if (in_order) {
+      auto row = [&](auto row_tag, float nk) -> float {
+        constexpr uint32_t OFF = (uint32_t)decltype(row_tag)::value * kYsRow;
+        float acc = 0.f;
 #pragma unroll
-          for (int e = 0; e < PER; ++e) {
-            const float2 ys = lds_f32x2(r.ysa[e] + koff);
-            const float R = fmaf(r.dxq[e], ys.y, ys.x);                         // :248 linear interpolation
-            acc = fmaf(r.wr[e], ex2_ftz(nk * r.Bh[e]) * R, acc);                // :264-265
-          }
-          part[c] = acc;
+        for (int e = 0; e < PER; ++e) {
+          const float2 ys = lds_f32x2_imm<OFF>(r.ysa[e]);
+          const float R = fmaf(r.dxq[e], ys.y, ys.x);                           // :248 linear interpolation
+          acc = fmaf(r.wr[e], ex2_ftz(nk * r.Bh[e]) * R, acc);                  // :264-265
         }
+        return acc;
+      };
+      // an absent channel keeps response and absorption 0 (:243, :251): the pixel is 0 * vol_c * F
+#define SNF_DT_ROW(c) if (present & (1u << c)) part[c] = row(std::integral_constant<int, c>{}, __shfl_sync(kFull, nk_lane, c))
+      SNF_DT_ROW(0); SNF_DT_ROW(1); SNF_DT_ROW(2); SNF_DT_ROW(3); SNF_DT_ROW(4); SNF_DT_ROW(5); SNF_DT_ROW(6);
+#undef SNF_DT_ROW
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float acc = 0.f;
+        if (c < C) {
+          const int k = __shfl_sync(kFull, k_lane, c);
+          const float nk = __shfl_sync(kFull, nk_lane, c);
+          if (k >= 0) {
+            const uint32_t koff = (uint32_t)k * kYsRow;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+              const float2 ys = lds_f32x2(r.ysa[e] + koff);
+              const float R = fmaf(r.dxq[e], ys.y, ys.x);
+              acc = fmaf(r.wr[e], ex2_ftz(nk * r.Bh[e]) * R, acc);
+            }
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) part[cc] = cc == c ? acc : part[cc];     // static register indices
       }
     }
     const float J = warp_sum8(part, lane);
@@ -834,32 +864,51 @@ __global__ void __launch_bounds__(kRayWarps * 32)
 #pragma unroll
     for (int e = 0; e < PER; ++e) s1[e] = dth[e] = dB[e] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      dkc[c] = 0.f;
-      if (c < C) {
-        const int k = __shfl_sync(kFull, k_lane, c);
-        const float kap = __shfl_sync(kFull, kap_lane, c), gi = __shfl_sync(kFull, gi_lane, c);
-        if (k >= 0) {   // absent channel: the pixel is the constant 0, no gradient to anything but vol_c (0 * F)
-          const float nk = -kap * 1.4426950408889634f;
-          const float Gc = gi * vc * F;            // dL/dJ with I = J * vol_c * F
-          const float hk = -0.5f * kap * Gc;       // dL/dB_k = hk u_k  (A = kappa B / 2, dL/dA_k = -Gc u_k)
-          const uint32_t koff = (uint32_t)k * kYsRow;
-          float part = 0.f, dk = 0.f;
+    for (int c = 0; c < 8; ++c) dkc[c] = 0.f;
+    // one channel's contribution; ROW >= 0: table row known at compile time (its offset is an immediate of the load)
+    auto channel = [&](auto row_tag, uint32_t koff, float kap, float gi) -> float {
+      constexpr int ROW = decltype(row_tag)::value;
+      const float nk = -kap * 1.4426950408889634f;
+      const float Gc = gi * vc * F;            // dL/dJ with I = J * vol_c * F
+      const float hk = -0.5f * kap * Gc;       // dL/dB_k = hk u_k  (A = kappa B / 2, dL/dA_k = -Gc u_k)
+      float part = 0.f, dk = 0.f;
 #pragma unroll
-          for (int e = 0; e < PER; ++e) {
-            const float2 ys = lds_f32x2(r.ysa[e] + koff);
-            const float R = fmaf(r.dxq[e], ys.y, ys.x);
-            const float eA = ex2_ftz(nk * r.Bh[e]);
-            const float u = r.wr[e] * (eA * R);    // w_k tau_k (0 outside the table and beyond the last trapezoid node)
-            part += u;
-            dB[e] = fmaf(hk, u, dB[e]);
-            dk = fmaf(r.Bh[e], u, dk);             // dL/dkappa = -Gc sum_k B_k / 2 u_k
-            s1[e] = fmaf(Gc, u, s1[e]);            // dL/drho_k (emission part) = 2 / rho_k sum_c Gc u_c
-            dth[e] = fmaf((Gc * eA) * r.wr[e], ys.y, dth[e]);   // dL/dtheta_k = sum_c Gc w_k rho_k^2 exp(-A) slope
-          }
-          gvc = fmaf(gi * F, part, gvc);
-          dkc[c] = -Gc * dk;
+      for (int e = 0; e < PER; ++e) {
+        float2 ys;
+        if constexpr (ROW >= 0) ys = lds_f32x2_imm<(uint32_t)(ROW >= 0 ? ROW : 0) * kYsRow>(r.ysa[e]);
+        else ys = lds_f32x2(r.ysa[e] + koff);
+        const float R = fmaf(r.dxq[e], ys.y, ys.x);
+        const float eA = ex2_ftz(nk * r.Bh[e]);
+        const float u = r.wr[e] * (eA * R);    // w_k tau_k (0 outside the table and beyond the last trapezoid node)
+        part += u;
+        dB[e] = fmaf(hk, u, dB[e]);
+        dk = fmaf(r.Bh[e], u, dk);             // dL/dkappa = -Gc sum_k B_k / 2 u_k
+        s1[e] = fmaf(Gc, u, s1[e]);            // dL/drho_k (emission part) = 2 / rho_k sum_c Gc u_c
+        dth[e] = fmaf((Gc * eA) * r.wr[e], ys.y, dth[e]);   // dL/dtheta_k = sum_c Gc w_k rho_k^2 exp(-A) slope
+      }
+      gvc = fmaf(gi * F, part, gvc);
+      return -Gc * dk;
+    };
+    // channels in table order wherever present (every shipped config; the STEREO mask only blanks entries): see the forward
+    const unsigned present = __ballot_sync(kFull, k_lane >= 0);
+    const bool in_order = __all_sync(kFull, k_lane < 0 || k_lane == lane);
+    if (in_order) {
+      // an absent channel's pixel is the constant 0: no gradient to anything but vol_c (0 * F)
+#define SNF_DT_ROW(c) \
+      if (present & (1u << c)) dkc[c] = channel(std::integral_constant<int, c>{}, 0u, __shfl_sync(kFull, kap_lane, c), __shfl_sync(kFull, gi_lane, c))
+      SNF_DT_ROW(0); SNF_DT_ROW(1); SNF_DT_ROW(2); SNF_DT_ROW(3); SNF_DT_ROW(4); SNF_DT_ROW(5); SNF_DT_ROW(6);
+#undef SNF_DT_ROW
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float dk = 0.f;
+        if (c < C) {
+          const int k = __shfl_sync(kFull, k_lane, c);
+          const float kap = __shfl_sync(kFull, kap_lane, c), gi = __shfl_sync(kFull, gi_lane, c);
+          if (k >= 0) dk = channel(std::integral_constant<int, -1>{}, (uint32_t)k * kYsRow, kap, gi);
         }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) dkc[cc] = cc == c ? dk : dkc[cc];          // static register indices
       }
     }
     // kappa gradients of this ray: lane l gets channel (l >> 2) & 7 summed over the warp, then one shared atomic per channel
@@ -890,7 +939,7 @@ __global__ void __launch_bounds__(kRayWarps * 32)
     for (int i = 0; i < PER; ++i) {
       const float Gp = i > 0 ? G[i > 0 ? i - 1 : 0] : (lane > 0 ? gup : 0.f);   // G of the previous sample (none at sample 0: dzp = 0)
       // d term_i / d rho_j: dz_j for i = j (dzn is 0 at S-1) and dz_{j-1} for i = j - 1
-      const float dr = s1[i] * (2.f / r.rho[i]) + r.dzn[i] * G[i] + r.dzp[i] * Gp;
+      const float dr = s1[i] * __fdividef(2.f, r.rho[i]) + r.dzn[i] * G[i] + r.dzp[i] * Gp;   // rho >= 1: the fast division is safe
       o[i].x = v[i].x > 0.f ? dr * r.rho[i] + greg[i] : 0.f;
       o[i].y = v[i].y > 0.f ? dth[i] : 0.f;
     }
