@@ -85,3 +85,27 @@ def test_render_workspace_size_is_host_arithmetic():
     d.S, d.kind = 64, 7
     assert L.snf_render_ws_bytes(ctypes.byref(d), 256, 0) == -1
     assert L.snf_render_ws_bytes(None, 256, 0) == -1
+
+
+def test_headers_are_plain_c():
+    """The boundary is a C ABI (`extern "C"`, plain pointers and sizes, no torch / CUDA types in the signatures): both headers
+    compile as C99 with nothing but the standard headers, and a C translation unit can take the address of every entry."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    inc = os.path.join(ROOT, 'include')
+    for h in ('sunerf_b200.h', 'sunerf_b200_debug.h'):
+        r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', os.path.join(inc, h)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    body = '#include "sunerf_b200.h"\n#include "sunerf_b200_debug.h"\nconst void *table[] = {\n' + \
+           ''.join(f'  (const void *)&{n},\n' for n in _declared()) + '};\nint main(void) { return table[0] == 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, 'use.c')
+        open(src, 'w').write(body)
+        r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', inc, '-c', src, '-o', os.path.join(d, 'use.o')],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
